@@ -1,0 +1,266 @@
+// C ABI entry points of the k-NN search (include/mepol_b200.h) and the search plan.
+#include <stdarg.h>
+#include <string.h>
+
+#include "knn_internal.cuh"
+
+namespace mepol {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached = sms;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+int mean_blocks_for(int64_t n_ref);
+
+static int simt_dpad(int d) {
+    const int opts[] = {4, 8, 16, 24, 32, 48, 64};
+    for (int o : opts)
+        if (d <= o) return o;
+    return -1;
+}
+
+// Fills the plan; with ws == nullptr only sizes are computed (pointers are offsets from null).
+int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d, int k1,
+                  int algo, void *ws) {
+    MEPOL_REQUIRE(n_ref > 0 && n_q > 0 && n_ref < (1LL << 31) && n_q < (1LL << 31), MEPOL_E_INVALID,
+                  "knn: n_ref=%lld n_q=%lld out of range", (long long)n_ref, (long long)n_q);
+    MEPOL_REQUIRE(d >= 1 && d <= MEPOL_MAX_DIM, MEPOL_E_INVALID, "knn: d=%d outside [1,%d]", d, MEPOL_MAX_DIM);
+    MEPOL_REQUIRE(k1 >= 1 && k1 <= MEPOL_MAX_K1, MEPOL_E_INVALID, "knn: k1=%d outside [1,%d]", k1, MEPOL_MAX_K1);
+    // mirrors sklearn's ValueError "Expected n_neighbors <= n_samples_fit" (neighbors/_base.py:834)
+    MEPOL_REQUIRE(k1 <= n_ref, MEPOL_E_INVALID, "knn: Expected n_neighbors <= n_samples_fit, got k1=%d n_ref=%lld",
+                  k1, (long long)n_ref);
+    MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC, MEPOL_E_INVALID,
+                  "knn: unknown algo %d", algo);
+    if (algo == MEPOL_KNN_AUTO) algo = (tc_supported(d, k1) && n_ref >= 4096) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
+    if (algo == MEPOL_KNN_TC && !tc_supported(d, k1)) {
+        set_error("knn: tensor-core pruner does not support d=%d k1=%d", d, k1);
+        return MEPOL_E_UNSUPPORTED;
+    }
+    memset(&p, 0, sizeof(p));
+    p.n_q = n_q;
+    p.n_ref = n_ref;
+    p.d = d;
+    p.k1 = k1;
+    p.algo = algo;
+    p.dpad = simt_dpad(d);
+    p.cap = k1 <= 8 ? 32 : (k1 <= 24 ? 64 : 128);
+    p.mean_blocks = mean_blocks_for(n_ref);
+    const int sms = device_sm_count();
+    if (algo == MEPOL_KNN_SIMT) {
+        p.rows_per_thread = (p.cap == 32 && p.dpad <= 32) ? 2 : 1;
+        p.rows_per_cta = kSimtThreads * p.rows_per_thread;
+        const int64_t row_tiles = (n_q + p.rows_per_cta - 1) / p.rows_per_cta;
+        int64_t want = (2LL * sms + row_tiles - 1) / row_tiles;
+        int64_t max_split = 1024 / p.cap;
+        if (max_split > 16) max_split = 16;
+        const int64_t ref_tiles = (n_ref + kSimtTileRefs - 1) / kSimtTileRefs;
+        if (max_split > ref_tiles / 4) max_split = ref_tiles / 4;
+        if (max_split < 1) max_split = 1;
+        p.n_split = (int)(want < 1 ? 1 : (want > max_split ? max_split : want));
+        // a query slice of the fitted matrix can reuse the packed reference rows
+        if (ref && q && q >= ref && q + n_q * d <= ref + n_ref * d && ((q - ref) % d) == 0) {
+            p.q_is_ref = true;
+            p.q_row0 = (q - ref) / d;
+        }
+    } else {
+        p.rows_per_thread = 1;
+        p.rows_per_cta = 256;
+        p.n_split = 1;
+        p.n_ref_pad = (n_ref + 127) / 128 * 128;
+        p.n_q_pad = (n_q + 255) / 256 * 256;
+    }
+    Carver c(ws);
+    p.mean_partial = c.take<double>((size_t)p.mean_blocks * MEPOL_MAX_DIM);
+    p.mean = c.take<double>(MEPOL_MAX_DIM);
+    p.glob = c.take<float>(G_COUNT);
+    p.stats = c.take<unsigned long long>(MEPOL_KNN_NSTATS);
+    p.r_anorm = c.take<float>((size_t)n_ref);
+    p.q_anorm = c.take<float>((size_t)n_q);
+    if (algo == MEPOL_KNN_SIMT) {
+        p.rs = c.take<float>((size_t)n_ref * p.dpad);
+        p.r_nrm = c.take<float>((size_t)n_ref);
+        if (p.q_is_ref) {
+            p.qs = ws ? p.rs + p.q_row0 * p.dpad : nullptr;
+            p.q_anorm = ws ? p.r_anorm + p.q_row0 : nullptr;
+        } else {
+            p.qs = c.take<float>((size_t)n_q * p.dpad);
+        }
+    } else {
+        p.rb = c.take<uint16_t>((size_t)p.n_ref_pad * kTcKPad);
+        p.qb = c.take<uint16_t>((size_t)p.n_q_pad * kTcKPad);
+        p.q_delta = c.take<float>((size_t)n_q);
+    }
+    p.cand = c.take<int32_t>((size_t)n_q * p.n_split * p.cap);
+    p.cand_cnt = c.take<int32_t>((size_t)n_q * p.n_split);
+    p.flag = c.take<unsigned char>((size_t)n_q);
+    p.bytes = c.bytes();
+    return MEPOL_OK;
+}
+
+// ---- optional per-launch timing of the dominant (prune) kernel, for bench.py's roofline -------
+constexpr int kProfSlots = 64;
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[kProfSlots][2];
+static bool g_prof_made = false;
+static int g_prof_count = 0;
+
+static void prof_record(int which, cudaStream_t st) {
+    if (!g_prof_on || g_prof_count >= kProfSlots) return;
+    if (!g_prof_made) {
+        for (int i = 0; i < kProfSlots; ++i) {
+            cudaEventCreate(&g_prof_ev[i][0]);
+            cudaEventCreate(&g_prof_ev[i][1]);
+        }
+        g_prof_made = true;
+    }
+    cudaEventRecord(g_prof_ev[g_prof_count][which], st);
+    if (which == 1) ++g_prof_count;
+}
+
+}  // namespace mepol
+
+using namespace mepol;
+
+extern "C" int mepol_profile_enable(int on) {
+    g_prof_on = on != 0;
+    g_prof_count = 0;
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_profile_read(float *ms_out, int max_n, int *n_out) {
+    MEPOL_REQUIRE(ms_out && n_out && max_n >= 0, MEPOL_E_INVALID, "profile_read: bad arguments");
+    int n = g_prof_count < max_n ? g_prof_count : max_n;
+    for (int i = 0; i < n; ++i) {
+        MEPOL_CUDA_CHECK(cudaEventSynchronize(g_prof_ev[i][1]));
+        MEPOL_CUDA_CHECK(cudaEventElapsedTime(ms_out + i, g_prof_ev[i][0], g_prof_ev[i][1]));
+    }
+    *n_out = n;
+    g_prof_count = 0;
+    return MEPOL_OK;
+}
+
+extern "C" const char *mepol_last_error(void) { return g_err; }
+extern "C" int mepol_version(void) { return 100; }
+
+extern "C" int mepol_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    MEPOL_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MEPOL_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_knn_workspace_bytes(int64_t n_q, int64_t n_ref, int d, int k1, int algo, size_t *bytes) {
+    MEPOL_REQUIRE(bytes != nullptr, MEPOL_E_INVALID, "knn_workspace_bytes: bytes is null");
+    KnnPlan p;
+    // worst case over aliasing: size as if the queries were packed separately
+    int rc = knn_make_plan(p, nullptr, n_ref, nullptr, n_q, d, k1, algo, nullptr);
+    if (rc != MEPOL_OK) return rc;
+    *bytes = p.bytes;
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d, int k1,
+                                    int algo, int32_t *idx_out, double *dist_out, double *rk_out, void *workspace,
+                                    size_t workspace_bytes, int64_t *stats, void *stream) {
+    MEPOL_REQUIRE(ref && q && idx_out && dist_out && workspace, MEPOL_E_INVALID, "knn_search: null pointer");
+    KnnPlan p;
+    int rc = knn_make_plan(p, ref, n_ref, q, n_q, d, k1, algo, workspace);
+    if (rc != MEPOL_OK) return rc;
+    MEPOL_REQUIRE(workspace_bytes >= p.bytes, MEPOL_E_WORKSPACE, "knn_search: workspace %zu < %zu bytes",
+                  workspace_bytes, p.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MEPOL_CUDA_CHECK(cudaMemsetAsync(p.flag, 0, (size_t)n_q, st));
+    MEPOL_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * MEPOL_KNN_NSTATS, st));
+    if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
+    if (!p.q_is_ref && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    prof_record(0, st);
+    if (p.algo == MEPOL_KNN_TC)
+        rc = launch_prune_tc(p, st);
+    else
+        rc = launch_prune_simt(p, st);
+    prof_record(1, st);
+    if (rc != MEPOL_OK) return rc;
+    if ((rc = launch_rerank(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_exact_fallback(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
+    if (stats)
+        MEPOL_CUDA_CHECK(cudaMemcpyAsync(stats, p.stats, sizeof(int64_t) * MEPOL_KNN_NSTATS,
+                                         cudaMemcpyDeviceToDevice, st));
+    return MEPOL_OK;
+}
+
+__global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+extern "C" int mepol_knn_search_host_f32(const float *x, int64_t n, int d, int k1, int algo, int64_t *idx_out,
+                                         double *dist_out) {
+    MEPOL_REQUIRE(x && idx_out && dist_out, MEPOL_E_INVALID, "knn_search_host: null pointer");
+    size_t ws_bytes = 0;
+    int rc = mepol_knn_workspace_bytes(n, n, d, k1, algo, &ws_bytes);
+    if (rc != MEPOL_OK) return rc;
+    float *dx = nullptr;
+    int32_t *didx = nullptr;
+    int64_t *didx64 = nullptr;
+    double *ddist = nullptr;
+    void *ws = nullptr;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dx);
+        cudaFree(didx);
+        cudaFree(didx64);
+        cudaFree(ddist);
+        cudaFree(ws);
+    };
+#define MEPOL_HOST_CHECK(expr)                                                                         \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                                 \
+            cleanup();                                                                                 \
+            return MEPOL_E_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+    MEPOL_HOST_CHECK(cudaMalloc(&dx, sizeof(float) * (size_t)n * d));
+    MEPOL_HOST_CHECK(cudaMalloc(&didx, sizeof(int32_t) * (size_t)n * k1));
+    MEPOL_HOST_CHECK(cudaMalloc(&didx64, sizeof(int64_t) * (size_t)n * k1));
+    MEPOL_HOST_CHECK(cudaMalloc(&ddist, sizeof(double) * (size_t)n * k1));
+    MEPOL_HOST_CHECK(cudaMalloc(&ws, ws_bytes));
+    MEPOL_HOST_CHECK(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, st));
+    rc = mepol_knn_search_f32(dx, n, dx, n, d, k1, algo, didx, ddist, nullptr, ws, ws_bytes, nullptr, st);
+    if (rc != MEPOL_OK) {
+        cleanup();
+        return rc;
+    }
+    const int64_t tot = n * (int64_t)k1;
+    widen_idx_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(didx, didx64, tot);
+    MEPOL_HOST_CHECK(cudaMemcpyAsync(idx_out, didx64, sizeof(int64_t) * (size_t)tot, cudaMemcpyDeviceToHost, st));
+    MEPOL_HOST_CHECK(cudaMemcpyAsync(dist_out, ddist, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, st));
+    MEPOL_HOST_CHECK(cudaStreamSynchronize(st));
+#undef MEPOL_HOST_CHECK
+    cleanup();
+    return MEPOL_OK;
+}

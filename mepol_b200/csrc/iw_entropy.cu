@@ -1,0 +1,523 @@
+// K2 / K3 / K4: importance-weighted k-NN entropy + KL (forward), its hand-written backward, and
+// the reverse-neighbour CSR that makes the backward a deterministic gather.
+//
+// Reference arithmetic being replaced (paths relative to /root/reference/):
+//   src/algorithms/mepol.py:121-138  u_j = exp(cumsum_t(lt - lb)) per trajectory, w = u / sum(u)
+//   src/algorithms/mepol.py:148      W_i = sum_{m<k} w[idx[i, m]]            (indices[:, :-1])
+//   src/algorithms/mepol.py:150      V_i = r_k^ns * pi^(ns/2) / Gamma(ns/2+1)
+//   src/algorithms/mepol.py:152      H   = -sum_i (W_i/k) log(W_i/(V_i+eps) + eps) + B
+//   src/algorithms/mepol.py:165      KL  = (1/N) sum_i log(k/(N W_i) + eps)
+//   loss.backward() (mepol.py:278)   closed form, SURVEY.md section 8a.
+//
+// Data flow (all arrays length N unless noted; T = float or double storage):
+//   iw_scan    (1 CTA / trajectory): c = segmented inclusive cumsum(lt - lb)            -> c[N]
+//              per-trajectory max m_t and sum exp(c - m_t); the LAST CTA to finish folds them into
+//              scal[3] = M = max c, scal[4] = S = sum exp(c - M)     (fixed order: deterministic)
+//   iw_gather  (1 thread / row): W_i = sum_m exp(c[idx[i,m]] - M)/S; row terms of H and KL;
+//              gW_i = dH/dW_i; block partials of {H, KL, sum gW_i W_i}; the last CTA reduces the
+//              partials in fixed order into scal[0..2].
+//   iw_bwd     (1 CTA / trajectory): g_w[j] = sum_{e in rev[j]} gW[col[e]]  (reverse CSR gather),
+//              g_c[j] = w_j (g_w[j] - s), grad_lt = grad_H * reverse segmented cumsum(g_c).
+//              s = sum_j g_w[j] w_j = sum_i gW_i W_i is already known from the forward, so the
+//              backward needs no grid-wide dependency.
+// Algorithmic HBM bytes per state at k=4, fp32 storage: scan 12, gather 8+8k+... see
+// DESIGN.md section "IW kernels".
+#include "common.cuh"
+
+namespace mepol {
+
+constexpr int kScanThreads = 256;
+constexpr int kGatherThreads = 256;
+constexpr double kLogPi = 1.1447298858494001741434273513531;
+
+struct IwWorkspace {
+    double *traj_max;   // [n_traj]
+    double *traj_sum;   // [n_traj]
+    double *blk_part;   // [n_gather_blocks * 4]
+    unsigned *counters; // [2] last-block-done tickets (zeroed by the forward launcher)
+    size_t bytes;
+};
+
+static int gather_blocks_for(int64_t n) { return (int)((n + kGatherThreads - 1) / kGatherThreads); }
+
+static void carve_iw(IwWorkspace &w, int64_t n, int64_t n_traj, void *ws) {
+    Carver c(ws);
+    w.traj_max = c.take<double>((size_t)n_traj);
+    w.traj_sum = c.take<double>((size_t)n_traj);
+    w.blk_part = c.take<double>((size_t)gather_blocks_for(n) * 4);
+    w.counters = c.take<unsigned>(4);
+    w.bytes = c.bytes();
+}
+
+// Block-wide inclusive scan of one value per thread (sum), returns the thread's inclusive prefix;
+// total over the block is left in *block_total (valid for every thread after the call).
+__device__ __forceinline__ double block_inclusive_scan(double v, double *s_warp, double *block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        s_warp[lane] = t;  // inclusive warp totals
+    }
+    __syncthreads();
+    const double prev = warp > 0 ? s_warp[warp - 1] : 0.0;
+    *block_total = s_warp[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return v + prev;
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double *s_warp) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;  // valid in warp 0
+}
+__device__ __forceinline__ double block_reduce_max(double v, double *s_warp) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    double t = -__longlong_as_double(0x7ff0000000000000LL);
+    if (warp == 0) {
+        t = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : t;
+        t = warp_max(t);
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------------------------ K2a scan
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads)
+    iw_scan_kernel(const T *__restrict__ lt, const T *__restrict__ lb, const int32_t *__restrict__ traj_off,
+                   int n_traj, T *__restrict__ c_out, double *__restrict__ traj_max,
+                   double *__restrict__ traj_sum, unsigned *__restrict__ counters, double *__restrict__ scal) {
+    __shared__ double s_warp[32];
+    __shared__ double s_bcast;
+    __shared__ unsigned s_ticket;
+    const int t = blockIdx.x;
+    const int lo = traj_off[t], hi = traj_off[t + 1];
+    const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
+    double carry = 0.0, local_max = NEG_INF;
+    for (int base = lo; base < hi; base += kScanThreads) {
+        const int j = base + threadIdx.x;
+        double dv = 0.0;
+        if (j < hi) dv = (double)lt[j] - (double)lb[j];
+        double total;
+        double incl = block_inclusive_scan(dv, s_warp, &total) + carry;
+        if (j < hi) {
+            const T stored = (T)incl;
+            c_out[j] = stored;
+            // NaN propagates: fmax would drop it, so track it explicitly via the sum below
+            local_max = fmax(local_max, (double)stored);
+        }
+        carry += total;
+    }
+    double m = block_reduce_max(local_max, s_warp);
+    if (threadIdx.x == 0) s_bcast = m;
+    __syncthreads();
+    m = s_bcast;
+    // second pass over the (L1/L2-resident) trajectory: sum exp(c - m_t)
+    double part = 0.0;
+    for (int j = lo + threadIdx.x; j < hi; j += kScanThreads) part += exp((double)c_out[j] - m);
+    part = block_reduce_sum(part, s_warp);
+    if (threadIdx.x == 0) {
+        traj_max[t] = m;
+        traj_sum[t] = (hi > lo) ? part : 0.0;
+        __threadfence();
+        s_ticket = atomicAdd(counters + 0, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != (unsigned)(n_traj - 1)) return;
+    // last CTA: fold per-trajectory (max, sum) pairs in fixed order
+    __threadfence();
+    double gm = NEG_INF;
+    for (int i = threadIdx.x; i < n_traj; i += kScanThreads) {
+        const double tm = ((volatile double *)traj_max)[i];
+        gm = fmax(gm, tm);
+    }
+    gm = block_reduce_max(gm, s_warp);
+    if (threadIdx.x == 0) s_bcast = gm;
+    __syncthreads();
+    gm = s_bcast;
+    double gs = 0.0;
+    for (int i = threadIdx.x; i < n_traj; i += kScanThreads) {
+        const double tm = ((volatile double *)traj_max)[i];
+        const double ts = ((volatile double *)traj_sum)[i];
+        if (ts != 0.0) gs += ts * exp(tm - gm);   // empty trajectories contribute 0 (NaN != 0 propagates)
+    }
+    gs = block_reduce_sum(gs, s_warp);
+    if (threadIdx.x == 0) {
+        scal[3] = gm;
+        scal[4] = gs;
+        // The reference forms exp(cumsum) directly in float64 (mepol.py:130): it overflows to inf
+        // (-> inf/inf = nan weights) above log(DBL_MAX) and the whole batch underflows to 0/0 below
+        // log(min subnormal).  The stabilised form here would silently survive; keep the reference's
+        // numeric-error behaviour by flagging those regimes.
+        scal[6] = (gm > 709.782712893384 || gm < -745.1332191019412) ? 1.0 : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------- K2b gather
+template <typename T>
+struct RowMath;
+template <>
+struct RowMath<float> {
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+};
+template <>
+struct RowMath<double> {
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kGatherThreads)
+    iw_gather_kernel(const T *__restrict__ c, const int32_t *__restrict__ idx, int k1, int n,
+                     const T *__restrict__ rk, int ns, double log_G, double B, double eps,
+                     T *__restrict__ gW, double *__restrict__ blk_part, unsigned *__restrict__ counters,
+                     double *__restrict__ scal) {
+    __shared__ double s_warp[32];
+    __shared__ unsigned s_ticket;
+    const int k = k1 - 1;
+    const int i = blockIdx.x * kGatherThreads + threadIdx.x;
+    const double M = scal[3], S = scal[4];
+    double h_term = 0.0, kl_term = 0.0, s_term = 0.0, bad = 0.0;
+    if (i < n) {
+        const int32_t *ir = idx + (size_t)i * k1;
+        // W_i in the storage precision's exp, accumulated in double
+        double W = 0.0;
+        const T Mt = (T)M;
+        for (int m = 0; m < k; ++m) W += (double)RowMath<T>::exp_(c[ir[m]] - Mt);
+        W /= S;
+        const double inv_k = 1.0 / (double)k;
+        double g;
+        if (eps == 0.0) {
+            // log-space: log q = log W - log V, log V = ns log r + (ns/2) log pi - lgamma(ns/2+1);
+            // r^ns overflows float32 already for ns=29, r>~20 -- never formed explicitly.
+            const T logW = RowMath<T>::log_((T)W);
+            const T logr = RowMath<T>::log_(rk[i]);
+            const double logV = (double)ns * (double)logr + 0.5 * (double)ns * kLogPi - log_G;
+            const double logq = (double)logW - logV;
+            h_term = (W * inv_k) * logq;
+            g = -inv_k * (logq + 1.0);
+            kl_term = log((double)k) - log((double)n) - (double)logW;
+        } else {
+            // literal float64 evaluation of mepol.py:150-152,165 (MountainCar's eps=1e-15)
+            const double r = (double)rk[i];
+            const double V = pow(r, (double)ns) * exp(0.5 * (double)ns * kLogPi) / exp(log_G);
+            const double qv = W / (V + eps);
+            h_term = (W * inv_k) * log(qv + eps);
+            g = -inv_k * (log(qv + eps) + qv / (qv + eps));
+            kl_term = log((double)k / ((double)n * W) + eps);
+        }
+        if (gW) gW[i] = (T)g;
+        s_term = g * W;
+        if (!(h_term == h_term) || !(kl_term == kl_term) || fabs(h_term) == INFINITY || fabs(kl_term) == INFINITY)
+            bad = 1.0;
+    }
+    const double bh = block_reduce_sum(h_term, s_warp);
+    const double bk = block_reduce_sum(kl_term, s_warp);
+    const double bs = block_reduce_sum(s_term, s_warp);
+    const double bb = block_reduce_sum(bad, s_warp);
+    if (threadIdx.x == 0) {
+        blk_part[(size_t)blockIdx.x * 4 + 0] = bh;
+        blk_part[(size_t)blockIdx.x * 4 + 1] = bk;
+        blk_part[(size_t)blockIdx.x * 4 + 2] = bs;
+        blk_part[(size_t)blockIdx.x * 4 + 3] = bb;
+        __threadfence();
+        s_ticket = atomicAdd(counters + 1, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kGatherThreads) {
+        const volatile double *pp = blk_part + (size_t)b * 4;
+        a0 += pp[0];
+        a1 += pp[1];
+        a2 += pp[2];
+        a3 += pp[3];
+    }
+    a0 = block_reduce_sum(a0, s_warp);
+    a1 = block_reduce_sum(a1, s_warp);
+    a2 = block_reduce_sum(a2, s_warp);
+    a3 = block_reduce_sum(a3, s_warp);
+    if (threadIdx.x == 0) {
+        const double poison = scal[6] != 0.0 ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+        scal[0] = -a0 + B + poison;          // H
+        scal[1] = a1 / (double)n + poison;   // KL before the max(0, .) clamp
+        scal[2] = a2;                 // s = sum_i gW_i W_i
+        scal[5] = a3;                 // rows whose terms were nan/inf
+        scal[7] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------- K3 bwd
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads)
+    iw_bwd_kernel(const T *__restrict__ c, const T *__restrict__ gW, const double *__restrict__ scal,
+                  const int32_t *__restrict__ traj_off, const int32_t *__restrict__ rowptr,
+                  const int32_t *__restrict__ col, const double *__restrict__ grad_H,
+                  T *__restrict__ grad_lt) {
+    __shared__ double s_warp[32];
+    const int t = blockIdx.x;
+    const int lo = traj_off[t], hi = traj_off[t + 1];
+    const double M = scal[3], S = scal[4], s = scal[2];
+    const double gH = grad_H[0];
+    const T Mt = (T)M;
+    double carry = 0.0;
+    // walk the trajectory backwards: position p = 0 is the LAST step
+    for (int base = 0; base < hi - lo; base += kScanThreads) {
+        const int p = base + threadIdx.x;
+        const int j = hi - 1 - p;
+        double gc = 0.0;
+        if (j >= lo) {
+            double gw = 0.0;
+            const int e0 = rowptr[j], e1 = rowptr[j + 1];
+            for (int e = e0; e < e1; ++e) gw += (double)gW[col[e]];
+            const double w = (double)RowMath<T>::exp_(c[j] - Mt) / S;
+            gc = w * (gw - s);
+        }
+        double total;
+        const double incl = block_inclusive_scan(gc, s_warp, &total) + carry;
+        if (j >= lo) grad_lt[j] = (T)(gH * incl);
+        carry += total;
+    }
+}
+
+// -------------------------------------------------------------------------------- K4 reverse CSR
+constexpr int kCsrThreads = 256;
+
+__global__ void csr_count_kernel(const int32_t *__restrict__ idx, int n, int k1, int32_t *__restrict__ deg) {
+    const int k = k1 - 1;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * k) return;
+    const int i = (int)(e / k), m = (int)(e % k);
+    atomicAdd(deg + idx[(size_t)i * k1 + m], 1);
+}
+
+// exclusive scan of deg[0..n) -> rowptr[0..n], three small kernels (block sums, scan of sums, add)
+__global__ void __launch_bounds__(kCsrThreads)
+    csr_block_sum_kernel(const int32_t *__restrict__ deg, int n, int items, int32_t *__restrict__ bsum) {
+    __shared__ int s[kCsrThreads / 32];
+    const int base = blockIdx.x * kCsrThreads * items;
+    int v = 0;
+    for (int it = 0; it < items; ++it) {
+        const int j = base + it * kCsrThreads + threadIdx.x;
+        if (j < n) v += deg[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kCsrThreads / 32; ++w) t += s[w];
+        bsum[blockIdx.x] = t;
+    }
+}
+__global__ void csr_scan_sums_kernel(int32_t *__restrict__ bsum, int nb) {
+    // single thread block, serial over a few thousand entries at most
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int v = bsum[b];
+            bsum[b] = run;
+            run += v;
+        }
+    }
+}
+__global__ void __launch_bounds__(kCsrThreads)
+    csr_finish_kernel(const int32_t *__restrict__ deg, int n, int items, const int32_t *__restrict__ bsum,
+                      int32_t *__restrict__ rowptr, int32_t *__restrict__ cursor) {
+    __shared__ int s_w[kCsrThreads / 32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = bsum[blockIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * kCsrThreads * items;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int it = 0; it < items; ++it) {
+        const int j = base + it * kCsrThreads + threadIdx.x;
+        const int v = j < n ? deg[j] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int prev = 0;
+        for (int w = 0; w < warp; ++w) prev += s_w[w];
+        int tot = 0;
+        for (int w = 0; w < kCsrThreads / 32; ++w) tot += s_w[w];
+        const int excl = s_carry + prev + incl - v;
+        if (j < n) {
+            rowptr[j] = excl;
+            cursor[j] = excl;
+        }
+        if (j == n - 1) rowptr[n] = excl + v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+}
+__global__ void csr_fill_kernel(const int32_t *__restrict__ idx, int n, int k1, int32_t *__restrict__ cursor,
+                                int32_t *__restrict__ col) {
+    const int k = k1 - 1;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * k) return;
+    const int i = (int)(e / k), m = (int)(e % k);
+    const int pos = atomicAdd(cursor + idx[(size_t)i * k1 + m], 1);
+    col[pos] = i;
+}
+// per-row insertion sort: atomics filled each row in arbitrary order; sorting makes the backward's
+// summation order (and therefore its bits) reproducible run to run.
+__global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ col) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int e0 = rowptr[j], e1 = rowptr[j + 1];
+    for (int a = e0 + 1; a < e1; ++a) {
+        const int v = col[a];
+        int b = a - 1;
+        while (b >= e0 && col[b] > v) {
+            col[b + 1] = col[b];
+            --b;
+        }
+        col[b + 1] = v;
+    }
+}
+
+constexpr int kCsrItems = 8;
+static int csr_blocks_for(int64_t n) { return (int)((n + (int64_t)kCsrThreads * kCsrItems - 1) / ((int64_t)kCsrThreads * kCsrItems)); }
+
+}  // namespace mepol
+
+using namespace mepol;
+
+extern "C" int mepol_rev_csr_workspace_bytes(int64_t n, int k, size_t *bytes) {
+    MEPOL_REQUIRE(bytes && n > 0 && k > 0, MEPOL_E_INVALID, "rev_csr_workspace_bytes: bad arguments");
+    Carver c(nullptr);
+    c.take<int32_t>((size_t)n + 1);               // deg
+    c.take<int32_t>((size_t)n + 1);               // cursor
+    c.take<int32_t>((size_t)csr_blocks_for(n) + 1);
+    *bytes = c.bytes();
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_rev_csr(const int32_t *idx, int64_t n, int k1, int32_t *rowptr, int32_t *col,
+                             void *workspace, size_t workspace_bytes, void *stream) {
+    MEPOL_REQUIRE(idx && rowptr && col && workspace, MEPOL_E_INVALID, "rev_csr: null pointer");
+    MEPOL_REQUIRE(n > 0 && k1 >= 2 && n * (int64_t)(k1 - 1) < (1LL << 31), MEPOL_E_INVALID,
+                  "rev_csr: need n > 0, k1 >= 2 and n*k < 2^31 (n=%lld k1=%d)", (long long)n, k1);
+    size_t need;
+    mepol_rev_csr_workspace_bytes(n, k1 - 1, &need);
+    MEPOL_REQUIRE(workspace_bytes >= need, MEPOL_E_WORKSPACE, "rev_csr: workspace %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Carver c(workspace);
+    int32_t *deg = c.take<int32_t>((size_t)n + 1);
+    int32_t *cursor = c.take<int32_t>((size_t)n + 1);
+    const int nb = csr_blocks_for(n);
+    int32_t *bsum = c.take<int32_t>((size_t)nb + 1);
+    const int k = k1 - 1;
+    MEPOL_CUDA_CHECK(cudaMemsetAsync(deg, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+    const int64_t edges = n * (int64_t)k;
+    const int eb = (int)((edges + 255) / 256);
+    csr_count_kernel<<<eb, 256, 0, st>>>(idx, (int)n, k1, deg);
+    csr_block_sum_kernel<<<nb, kCsrThreads, 0, st>>>(deg, (int)n, kCsrItems, bsum);
+    csr_scan_sums_kernel<<<1, 32, 0, st>>>(bsum, nb);
+    csr_finish_kernel<<<nb, kCsrThreads, 0, st>>>(deg, (int)n, kCsrItems, bsum, rowptr, cursor);
+    csr_fill_kernel<<<eb, 256, 0, st>>>(idx, (int)n, k1, cursor, col);
+    csr_sort_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(rowptr, (int)n, col);
+    MEPOL_CUDA_CHECK(cudaGetLastError());
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_iw_workspace_bytes(int64_t n, int64_t n_traj, size_t *bytes) {
+    MEPOL_REQUIRE(bytes && n > 0 && n_traj > 0, MEPOL_E_INVALID, "iw_workspace_bytes: bad arguments");
+    IwWorkspace w;
+    carve_iw(w, n, n_traj, nullptr);
+    *bytes = w.bytes;
+    return MEPOL_OK;
+}
+
+template <typename T>
+static int iw_fwd_impl(const T *lt, const T *lb, const int32_t *traj_off, int64_t n_traj, int64_t n,
+                       const int32_t *idx, int k1, const T *rk, int ns, double log_G, double B, double eps,
+                       T *c, T *gW, double *scal, void *workspace, size_t workspace_bytes, void *stream) {
+    MEPOL_REQUIRE(lt && lb && traj_off && idx && rk && c && scal && workspace, MEPOL_E_INVALID,
+                  "iw_entropy_fwd: null pointer");
+    MEPOL_REQUIRE(n > 0 && n < (1LL << 31) && n_traj > 0 && n_traj <= n && k1 >= 2 && ns > 0, MEPOL_E_INVALID,
+                  "iw_entropy_fwd: bad sizes n=%lld n_traj=%lld k1=%d ns=%d", (long long)n, (long long)n_traj, k1, ns);
+    IwWorkspace w;
+    carve_iw(w, n, n_traj, workspace);
+    MEPOL_REQUIRE(workspace_bytes >= w.bytes, MEPOL_E_WORKSPACE, "iw_entropy_fwd: workspace %zu < %zu",
+                  workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MEPOL_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, 4 * sizeof(unsigned), st));
+    iw_scan_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(lt, lb, traj_off, (int)n_traj, c, w.traj_max,
+                                                            w.traj_sum, w.counters, scal);
+    iw_gather_kernel<T><<<gather_blocks_for(n), kGatherThreads, 0, st>>>(
+        c, idx, k1, (int)n, rk, ns, log_G, B, eps, gW, w.blk_part, w.counters, scal);
+    MEPOL_CUDA_CHECK(cudaGetLastError());
+    return MEPOL_OK;
+}
+
+template <typename T>
+static int iw_bwd_impl(const T *c, const T *gW, const double *scal, const int32_t *traj_off, int64_t n_traj,
+                       int64_t n, const int32_t *rowptr, const int32_t *col, const double *grad_H, T *grad_lt,
+                       void *stream) {
+    MEPOL_REQUIRE(c && gW && scal && traj_off && rowptr && col && grad_H && grad_lt, MEPOL_E_INVALID,
+                  "iw_entropy_bwd: null pointer");
+    MEPOL_REQUIRE(n > 0 && n_traj > 0, MEPOL_E_INVALID, "iw_entropy_bwd: bad sizes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    iw_bwd_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(c, gW, scal, traj_off, rowptr, col, grad_H, grad_lt);
+    MEPOL_CUDA_CHECK(cudaGetLastError());
+    return MEPOL_OK;
+}
+
+extern "C" int mepol_iw_entropy_fwd_f32(const float *logp_t, const float *logp_b, const int32_t *traj_off,
+                                        int64_t n_traj, int64_t n, const int32_t *idx, int k1, const float *rk,
+                                        int ns, double log_G, double B, double eps, float *c, float *gW,
+                                        double *scal, void *workspace, size_t workspace_bytes, void *stream) {
+    return iw_fwd_impl<float>(logp_t, logp_b, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, c, gW, scal,
+                              workspace, workspace_bytes, stream);
+}
+extern "C" int mepol_iw_entropy_fwd_f64(const double *logp_t, const double *logp_b, const int32_t *traj_off,
+                                        int64_t n_traj, int64_t n, const int32_t *idx, int k1, const double *rk,
+                                        int ns, double log_G, double B, double eps, double *c, double *gW,
+                                        double *scal, void *workspace, size_t workspace_bytes, void *stream) {
+    return iw_fwd_impl<double>(logp_t, logp_b, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, c, gW, scal,
+                               workspace, workspace_bytes, stream);
+}
+extern "C" int mepol_iw_entropy_bwd_f32(const float *c, const float *gW, const double *scal,
+                                        const int32_t *traj_off, int64_t n_traj, int64_t n,
+                                        const int32_t *rowptr, const int32_t *col, const double *grad_H,
+                                        float *grad_logp_t, void *stream) {
+    return iw_bwd_impl<float>(c, gW, scal, traj_off, n_traj, n, rowptr, col, grad_H, grad_logp_t, stream);
+}
+extern "C" int mepol_iw_entropy_bwd_f64(const double *c, const double *gW, const double *scal,
+                                        const int32_t *traj_off, int64_t n_traj, int64_t n,
+                                        const int32_t *rowptr, const int32_t *col, const double *grad_H,
+                                        double *grad_logp_t, void *stream) {
+    return iw_bwd_impl<double>(c, gW, scal, traj_off, n_traj, n, rowptr, col, grad_H, grad_logp_t, stream);
+}

@@ -1,0 +1,128 @@
+// Internal plan / launcher declarations of the exact k-NN search (prep -> prune -> re-rank -> fallback).
+#pragma once
+#include "common.cuh"
+
+namespace mepol {
+
+constexpr int kSimtThreads = 128;  // one query row (or two) per thread
+constexpr int kSimtTileRefs = 64;  // reference rows staged per shared-memory tile
+constexpr int kTcKPad = 32;        // bf16 operand width of the tensor-core pruner (d + 3 norm columns <= 32)
+
+// indices into the float "glob" array produced by the pack kernels (stored as uint bits, atomicMax)
+enum { G_AMAX = 0, G_DELTA_MAX = 1, G_ATILDE_MAX = 2, G_COUNT = 4 };
+
+struct KnnPlan {
+    int64_t n_q, n_ref;
+    int d, k1, algo;
+    int dpad;          // SIMT operand width (multiple of 4)
+    int rows_per_thread;
+    int rows_per_cta;
+    int cap;           // candidate slots per (row, split)
+    int n_split;       // reference-range splits (more CTAs for small batches)
+    int mean_blocks;
+    bool q_is_ref;     // query rows alias the packed reference rows
+    int64_t q_row0;    // first reference row of the query slice when q_is_ref
+    // workspace slices
+    double *mean_partial, *mean;
+    float *rs, *r_nrm, *r_anorm, *qs, *q_anorm;
+    float *glob;
+    int32_t *cand, *cand_cnt;
+    unsigned char *flag;
+    unsigned long long *stats;
+    // tensor-core pruner operands (bf16 stored as uint16), padded to tile multiples
+    uint16_t *rb, *qb;
+    float *q_delta;
+    int64_t n_ref_pad, n_q_pad;
+    size_t bytes;
+};
+
+int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d,
+                  int k1, int algo, void *ws);
+
+// knn_prep.cu
+int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cudaStream_t st);
+int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, cudaStream_t st);
+// knn_simt.cu
+int launch_prune_simt(const KnnPlan &p, cudaStream_t st);
+// knn_tc.cu
+bool tc_supported(int d, int k1);
+int launch_prune_tc(const KnnPlan &p, cudaStream_t st);
+// knn_rerank.cu
+int launch_rerank(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
+                  double *dist_out, double *rk_out, cudaStream_t st);
+int launch_exact_fallback(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
+                          double *dist_out, double *rk_out, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// Per-row candidate buffer shared by both pruners.  Each thread owns one query row; its buffer is
+// a column of a [cap][rows] shared-memory array (stride = rows, so a warp touching slot e of 32
+// different rows hits 32 different banks).
+//
+// Safety argument (DESIGN.md "pruning band"): let e bound |approx score - true score| for this
+// row.  With t = k1-th smallest approximate score seen so far, any reference whose approximate
+// score exceeds t + 2e has k1 references strictly closer in exact arithmetic, so it can never be
+// one of the k1 nearest -- dropping it is exact.  compact() re-derives t from the buffer, tightens
+// tau = t + band (band = 2e) and drops entries above it.  If the buffer stays full the row is
+// flagged for the exact fallback kernel.
+// ------------------------------------------------------------------------------------------
+struct RowBuf {
+    float *v;   // scores, element e at v[e * stride]
+    int *ix;    // reference indices
+    int stride;
+};
+
+__device__ __noinline__ static void rowbuf_compact(RowBuf b, int &cnt, float &tau, int k1, float band,
+                                                   int cap, bool &overflow) {
+    float t = __int_as_float(0x7f800000);  // +inf when fewer than k1 entries
+    if (cnt >= k1) {
+        float last_v = -__int_as_float(0x7f800000);
+        int last_p = -1;
+        for (int m = 0; m < k1; ++m) {
+            float best = __int_as_float(0x7f800000);
+            int bp = cnt;
+            for (int p = 0; p < cnt; ++p) {
+                float x = b.v[p * b.stride];
+                bool after = (x > last_v) || (x == last_v && p > last_p);
+                if (after && x < best) {
+                    best = x;
+                    bp = p;
+                }
+            }
+            last_v = best;
+            last_p = bp;
+        }
+        t = last_v;
+    }
+    float new_tau = t + band;
+    if (new_tau < tau) tau = new_tau;
+    int w = 0;
+    for (int p = 0; p < cnt; ++p) {
+        float x = b.v[p * b.stride];
+        int id = b.ix[p * b.stride];
+        if (x <= tau) {
+            b.v[w * b.stride] = x;
+            b.ix[w * b.stride] = id;
+            ++w;
+        }
+    }
+    cnt = w;
+    if (cnt >= cap) {
+        overflow = true;
+        cnt = 0;
+        tau = -__int_as_float(0x7f800000);  // nothing more is collected for a flagged row
+    }
+}
+
+__device__ __forceinline__ void rowbuf_push(RowBuf b, int &cnt, float &tau, float score, int ref_idx,
+                                            int k1, float band, int cap, bool &overflow,
+                                            unsigned &n_compactions) {
+    b.v[cnt * b.stride] = score;
+    b.ix[cnt * b.stride] = ref_idx;
+    ++cnt;
+    if (cnt == cap) {
+        rowbuf_compact(b, cnt, tau, k1, band, cap, overflow);
+        ++n_compactions;
+    }
+}
+
+}  // namespace mepol

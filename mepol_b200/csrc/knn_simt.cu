@@ -1,0 +1,216 @@
+// K1 (SIMT form): fp32 pruning pass of the exact k-NN search.
+//
+// Replaces the hot loop of sklearn's brute ArgKmin
+// (sklearn/metrics/_pairwise_distances_reduction/_argkmin.pyx.tp:471-510: GEMM middle term + norms
+//  + heap_push for every (query, reference) pair).  Used for small particle dimensions (the
+// GridWorld / MountainCar / Ant-7d configs, where a 2..7-wide contraction cannot feed tensor
+// cores), for k+1 > 12 and as the always-available path; knn_tc.cu is the tcgen05 form.
+//
+// Work decomposition: one thread owns ROWS query rows (their centred coordinates live in
+// registers) and streams over reference tiles staged in shared memory with cp.async double
+// buffering; every lane of a warp reads the same reference element, so the tile reads are
+// conflict-free broadcasts.  The score  s = ||y'||^2 - 2 x'.y'  (the row-constant ||x'||^2 is
+// dropped) is compared against the row's pruning threshold; survivors go to the row's candidate
+// buffer (knn_internal.cuh).  Exactness comes from the error band + fp64 re-rank, not from fp32.
+#include "knn_internal.cuh"
+
+namespace mepol {
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// fp32 error bound of the score for a row with centred norm a (A = max reference norm), u = 2^-24:
+//   |fl(x^.y^) - x'.y'| <= (2u + u^2) a A + gamma_d (1+u)^2 a A,   |n^ - ||y'||^2| <= u A^2,
+//   final fma rounding <= u (A^2 + 2 a A).   e <= u((2d + 6) a A + 2 A^2); 1.25x slack on top.
+__device__ __forceinline__ float simt_band(float a, float A, int d) {
+    const float u = 5.9604645e-8f;
+    float e = 1.25f * u * ((2.0f * d + 6.0f) * a * A + 2.0f * A * A);
+    return 2.0f * e + 1e-37f;
+}
+
+template <int DPAD, int ROWS>
+__global__ void __launch_bounds__(kSimtThreads)
+    knn_prune_simt_kernel(const float *__restrict__ qs, const float *__restrict__ q_anorm, int n_q,
+                          const float *__restrict__ rs, const float *__restrict__ r_nrm, int n_ref,
+                          const float *__restrict__ glob, int d_true, int k1, int cap, int n_split,
+                          int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt,
+                          unsigned char *__restrict__ flag, unsigned long long *__restrict__ stats) {
+    constexpr int R = kSimtThreads * ROWS;
+    constexpr int BN = kSimtTileRefs;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);                 // [2][BN][DPAD]
+    float *tnrm = tile + 2 * BN * DPAD;                                // [2][BN]
+    float *bufv = tnrm + 2 * BN;                                       // [cap][R]
+    int *bufi = reinterpret_cast<int *>(bufv + (size_t)cap * R);       // [cap][R]
+
+    const int tid = threadIdx.x;
+    const int split = blockIdx.y;
+    // reference range of this split, in whole tiles
+    const int tiles_total = (n_ref + BN - 1) / BN;
+    const int tiles_per = (tiles_total + n_split - 1) / n_split;
+    const int tile_lo = split * tiles_per;
+    int tile_hi = tile_lo + tiles_per;
+    if (tile_hi > tiles_total) tile_hi = tiles_total;
+
+    float q[ROWS][DPAD];
+    float tau[ROWS], band[ROWS];
+    int cnt[ROWS];
+    bool ovf[ROWS];
+    int row[ROWS];
+    const float A = glob[G_AMAX];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        row[r] = blockIdx.x * R + r * kSimtThreads + tid;
+        const int rr = row[r] < n_q ? row[r] : n_q - 1;   // clamp: tail threads redo the last row
+        const float4 *src = reinterpret_cast<const float4 *>(qs + (size_t)rr * DPAD);
+#pragma unroll
+        for (int c = 0; c < DPAD / 4; ++c) {
+            float4 v = src[c];
+            q[r][4 * c] = v.x; q[r][4 * c + 1] = v.y; q[r][4 * c + 2] = v.z; q[r][4 * c + 3] = v.w;
+        }
+        tau[r] = __int_as_float(0x7f800000);
+        band[r] = simt_band(q_anorm[rr], A, d_true);
+        cnt[r] = 0;
+        ovf[r] = false;
+    }
+    unsigned n_compactions = 0;
+
+    auto load_tile = [&](int t, int stage) {
+        const int ref0 = t * BN;
+        float *dst = tile + stage * BN * DPAD;
+        constexpr int VEC = BN * DPAD / 4;
+        for (int v = tid; v < VEC; v += kSimtThreads) {
+            int rj = (v * 4) / DPAD;
+            int src_row = ref0 + rj < n_ref ? ref0 + rj : n_ref - 1;
+            cp_async16(dst + v * 4, rs + (size_t)src_row * DPAD + (v * 4) % DPAD);
+        }
+        if (tid < BN) {
+            int src_row = ref0 + tid;
+            // out-of-range references get an infinite norm -> score +inf -> never collected
+            tnrm[stage * BN + tid] = src_row < n_ref ? r_nrm[src_row] : __int_as_float(0x7f800000);
+        }
+    };
+
+    if (tile_lo < tile_hi) load_tile(tile_lo, 0);
+    cp_async_commit();
+    for (int t = tile_lo; t < tile_hi; ++t) {
+        const int stage = (t - tile_lo) & 1;
+        if (t + 1 < tile_hi) load_tile(t + 1, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const float *ts = tile + stage * BN * DPAD;
+        const float *tn = tnrm + stage * BN;
+        const int ref0 = t * BN;
+#pragma unroll 1
+        for (int j0 = 0; j0 < BN; j0 += 4) {
+            float acc[ROWS][4];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[r][jj] = 0.f;
+#pragma unroll
+            for (int c = 0; c < DPAD; c += 4) {
+                float4 y[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    y[jj] = *reinterpret_cast<const float4 *>(ts + (j0 + jj) * DPAD + c);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        acc[r][jj] = fmaf(q[r][c], y[jj].x, acc[r][jj]);
+                        acc[r][jj] = fmaf(q[r][c + 1], y[jj].y, acc[r][jj]);
+                        acc[r][jj] = fmaf(q[r][c + 2], y[jj].z, acc[r][jj]);
+                        acc[r][jj] = fmaf(q[r][c + 3], y[jj].w, acc[r][jj]);
+                    }
+            }
+            const float4 nn = *reinterpret_cast<const float4 *>(tn + j0);
+            const float nv[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float s = fmaf(-2.0f, acc[r][jj], nv[jj]);
+                    if (s < tau[r]) {   // strict: +inf scores of padding references never enter
+                        RowBuf b{bufv + r * kSimtThreads + tid, bufi + r * kSimtThreads + tid, R};
+                        rowbuf_push(b, cnt[r], tau[r], s, ref0 + j0 + jj, k1, band[r], cap, ovf[r],
+                                    n_compactions);
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+    unsigned long long n_cand = 0;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (row[r] >= n_q) continue;
+        RowBuf b{bufv + r * kSimtThreads + tid, bufi + r * kSimtThreads + tid, R};
+        if (!ovf[r] && cnt[r] > k1) rowbuf_compact(b, cnt[r], tau[r], k1, band[r], cap, ovf[r]);
+        const size_t slot = (size_t)row[r] * n_split + split;
+        if (ovf[r]) {
+            flag[row[r]] = 1;
+            cand_cnt[slot] = 0;
+        } else {
+            cand_cnt[slot] = cnt[r];
+            int32_t *dst = cand + slot * cap;
+            for (int e = 0; e < cnt[r]; ++e) dst[e] = b.ix[e * R];
+            n_cand += cnt[r];
+        }
+    }
+    if (stats) {
+        n_cand = (unsigned long long)warp_sum((double)n_cand);
+        unsigned long long nc = (unsigned long long)warp_sum((double)n_compactions);
+        if ((tid & 31) == 0) {
+            atomicAdd(stats + 0, n_cand);
+            atomicAdd(stats + 2, nc);
+        }
+    }
+}
+
+template <int DPAD, int ROWS>
+static int launch_simt_inst(const KnnPlan &p, cudaStream_t st) {
+    const int R = kSimtThreads * ROWS;
+    const size_t smem = (size_t)(2 * kSimtTileRefs * DPAD + 2 * kSimtTileRefs) * 4 + (size_t)p.cap * R * 8;
+    auto kern = knn_prune_simt_kernel<DPAD, ROWS>;
+    MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.n_q + R - 1) / R), (unsigned)p.n_split);
+    kern<<<grid, kSimtThreads, smem, st>>>(p.qs, p.q_anorm, (int)p.n_q, p.rs, p.r_nrm, (int)p.n_ref,
+                                           p.glob, p.d, p.k1, p.cap, p.n_split, p.cand, p.cand_cnt,
+                                           p.flag, p.stats);
+    MEPOL_CUDA_CHECK(cudaGetLastError());
+    return MEPOL_OK;
+}
+
+int launch_prune_simt(const KnnPlan &p, cudaStream_t st) {
+#define MEPOL_SIMT_CASE(DP)                                                       \
+    case DP:                                                                      \
+        return p.rows_per_thread == 2 ? launch_simt_inst<DP, 2>(p, st) : launch_simt_inst<DP, 1>(p, st);
+    switch (p.dpad) {
+        MEPOL_SIMT_CASE(4)
+        MEPOL_SIMT_CASE(8)
+        MEPOL_SIMT_CASE(16)
+        MEPOL_SIMT_CASE(24)
+        MEPOL_SIMT_CASE(32)
+        case 48:
+            return launch_simt_inst<48, 1>(p, st);
+        case 64:
+            return launch_simt_inst<64, 1>(p, st);
+        default:
+            break;
+    }
+#undef MEPOL_SIMT_CASE
+    set_error("knn simt: unsupported padded dimension %d", p.dpad);
+    return MEPOL_E_UNSUPPORTED;
+}
+
+}  // namespace mepol

@@ -1,0 +1,376 @@
+"""Host side of the importance-weighted k-NN entropy / KL objective.
+
+Mirrors, with the same names, argument order and return conventions, the module-level functions
+of /root/reference/src/algorithms/mepol.py that `mepol()` calls:
+
+    compute_importance_weights  :114-139     compute_entropy :142-154
+    compute_kl                  :157-174     policy_update   :268-281
+
+Policies stay the reference's CPU float64 `GaussianPolicy` modules (src/policy.py:11-61) and the
+optimiser stays a CPU torch optimiser; results come back as CPU 0-dim float64 tensors that support
+`.backward()`, `.detach()`, `.numpy()`, `torch.isnan`.
+Underneath: parameters are mirrored to the GPU, the MLP log-probs run in torch on the device
+(cuBLAS, float64 by default), and everything from the log-probs to the entropy, the KL and the
+gradient w.r.t. the log-probs runs in the hand-written kernels of libmepol_b200.so through
+`IWEntropyFunction` (a torch.autograd.Function).  No CPU fallback.
+"""
+import math
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from .knn import _stream_ptr
+
+POLICY_EPS = 1e-7          # src/utils/dtypes.py:7, used inside get_log_p's variance term only
+_LOG_2PI = math.log(2.0 * math.pi)
+
+_config = {"compute_dtype": torch.float64, "burn_rng": True, "device": None}
+
+
+def configure(compute_dtype=None, burn_rng=None, device=None):
+    """compute_dtype: torch.float64 (default, reproduces the float64 reference to ~1e-12) or
+    torch.float32 (the bandwidth-optimal kernels; 1e-5 relative).  burn_rng: consume the same
+    torch.randn draws the reference's get_log_p burns so seeded runs stay aligned."""
+    if compute_dtype is not None:
+        if compute_dtype not in (torch.float32, torch.float64):
+            raise ValueError("compute_dtype must be torch.float32 or torch.float64")
+        _config["compute_dtype"] = compute_dtype
+    if burn_rng is not None:
+        _config["burn_rng"] = bool(burn_rng)
+    if device is not None:
+        _config["device"] = torch.device(device)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.MepolError("mepol_b200 needs a CUDA device (there is no CPU fallback)")
+    return _config["device"] or torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------- device handles
+class SearchHandle:
+    """Device-resident view of one k-NN search result, shared by every objective evaluation of an
+    epoch: int32 indices, the k-th-neighbour radius column, trajectory offsets and (lazily) the
+    reverse-neighbour CSR used by the backward."""
+
+    def __init__(self, idx_i32, rk_f64, k1):
+        self.idx = idx_i32.contiguous()
+        self.k1 = int(k1)
+        self.n = int(idx_i32.shape[0])
+        self._rk = {torch.float64: rk_f64.contiguous()}
+        self._csr = None
+        self._ws = None
+
+    def rk(self, dtype):
+        if dtype not in self._rk:
+            self._rk[dtype] = self._rk[torch.float64].to(dtype)
+        return self._rk[dtype]
+
+    def csr(self):
+        if self._csr is None:
+            dev = self.idx.device
+            k = self.k1 - 1
+            with torch.cuda.device(dev):
+                rowptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+                col = torch.empty(self.n * k, dtype=torch.int32, device=dev)
+                ws = torch.empty(_lib.rev_csr_workspace_bytes(self.n, k), dtype=torch.uint8, device=dev)
+                rc = _lib.load().mepol_rev_csr(self.idx.data_ptr(), self.n, self.k1, rowptr.data_ptr(),
+                                               col.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc, "mepol_rev_csr")
+            self._csr = (rowptr, col)
+            self._ws = ws
+        return self._csr
+
+
+def traj_offsets(real_traj_lengths, device):
+    lens = torch.as_tensor(real_traj_lengths).reshape(-1).to(torch.int64).cpu()
+    off = torch.zeros(lens.numel() + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens, 0)
+    return off.to(torch.int32).to(device), int(off[-1])
+
+
+# ------------------------------------------------------------------------------- autograd bridge
+class IWEntropyFunction(torch.autograd.Function):
+    """(H, KL_raw, n_bad) = f(logp_target, logp_behav) through the fused CUDA kernels.
+
+    forward  -> mepol_iw_entropy_fwd_{f32,f64}   (replaces mepol.py:121-152 and :159-165)
+    backward -> mepol_iw_entropy_bwd_{f32,f64}   (replaces autograd of the same lines)"""
+
+    @staticmethod
+    def forward(ctx, logp_t, logp_b, handle, traj_off, n_traj, k, ns, log_G, B, eps):
+        if not logp_t.is_cuda:
+            raise _lib.MepolError("IWEntropyFunction needs CUDA tensors (there is no CPU fallback)")
+        dt = logp_t.dtype
+        if dt not in (torch.float32, torch.float64):
+            raise ValueError("log-probs must be float32 or float64")
+        lt = logp_t.detach().contiguous()
+        lb = logp_b.detach().to(dt).contiguous()
+        n = lt.numel()
+        if n != handle.n or handle.k1 != k + 1:
+            raise ValueError(f"log-probs ({n}) do not match the search result ({handle.n} rows, k1={handle.k1})")
+        dev = lt.device
+        need_grad = any(ctx.needs_input_grad[:2])
+        lib = _lib.load()
+        suffix = "f32" if dt == torch.float32 else "f64"
+        with torch.cuda.device(dev):
+            c = torch.empty(n, dtype=dt, device=dev)
+            gW = torch.empty(n, dtype=dt, device=dev) if need_grad else None
+            scal = torch.empty(8, dtype=torch.float64, device=dev)
+            ws = torch.empty(_lib.iw_workspace_bytes(n, n_traj), dtype=torch.uint8, device=dev)
+            fn = getattr(lib, "mepol_iw_entropy_fwd_" + suffix)
+            rc = fn(lt.data_ptr(), lb.data_ptr(), traj_off.data_ptr(), n_traj, n, handle.idx.data_ptr(),
+                    handle.k1, handle.rk(dt).data_ptr(), int(ns), float(log_G), float(B), float(eps),
+                    c.data_ptr(), gW.data_ptr() if need_grad else None, scal.data_ptr(), ws.data_ptr(),
+                    ws.numel(), _stream_ptr(dev))
+            _lib.check(rc, "mepol_iw_entropy_fwd_" + suffix)
+        ctx.handle, ctx.traj_off, ctx.n_traj, ctx.suffix = handle, traj_off, n_traj, suffix
+        ctx.save_for_backward(c, gW if need_grad else c, scal)
+        ctx.keep = ws
+        H, kl_raw, n_bad = scal[0].clone(), scal[1].clone(), scal[5].clone()
+        ctx.mark_non_differentiable(kl_raw, n_bad)
+        return H, kl_raw, n_bad
+
+    @staticmethod
+    def backward(ctx, grad_H, _gkl, _gbad):
+        c, gW, scal = ctx.saved_tensors
+        handle = ctx.handle
+        dev = c.device
+        n = c.numel()
+        rowptr, col = handle.csr()
+        g = grad_H.detach().to(torch.float64).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            out = torch.empty(n, dtype=c.dtype, device=dev)
+            fn = getattr(_lib.load(), "mepol_iw_entropy_bwd_" + ctx.suffix)
+            rc = fn(c.data_ptr(), gW.data_ptr(), scal.data_ptr(), ctx.traj_off.data_ptr(), ctx.n_traj, n,
+                    rowptr.data_ptr(), col.data_ptr(), g.data_ptr(), out.data_ptr(), _stream_ptr(dev))
+            _lib.check(rc, "mepol_iw_entropy_bwd_" + ctx.suffix)
+        g_t = out if ctx.needs_input_grad[0] else None
+        g_b = -out if ctx.needs_input_grad[1] else None
+        return g_t, g_b, None, None, None, None, None, None, None, None
+
+
+def iw_entropy(logp_t, logp_b, handle, traj_off, n_traj, k, ns, G, B, eps):
+    """Device-level objective: returns (H, KL_raw, n_bad_rows) as 0-dim CUDA float64 tensors."""
+    return IWEntropyFunction.apply(logp_t, logp_b, handle, traj_off, int(n_traj), int(k), int(ns),
+                                   math.lgamma(ns / 2.0 + 1.0) if G is None else math.log(G), float(B), float(eps))
+
+
+# ------------------------------------------------------------------------------- policy mirror
+def _policy_layers(policy):
+    """(list of hidden (Linear, activation) pairs, mean Linear, log_std) of a GaussianPolicy-shaped
+    module (src/policy.py:17-29): `net` = Sequential(Linear, act, Linear, act, ...), `mean`, `log_std`."""
+    mods = list(policy.net)
+    return mods, policy.mean, policy.log_std
+
+
+def mirror_params(policy, device, dtype, requires_grad):
+    out = []
+    for p in policy.parameters():
+        t = p.detach().to(device=device, dtype=dtype)
+        out.append(t.requires_grad_(requires_grad))
+    return out
+
+
+def gaussian_log_p(policy, params, states, actions):
+    """policy.py:43-61 on device tensors with mirrored parameters `params` (ordered like
+    policy.parameters(): log_std first, then net.*, then mean.*)."""
+    names = [n for n, _ in policy.named_parameters()]
+    table = dict(zip(names, params))
+    h = states
+    for i, m in enumerate(policy.net):
+        if isinstance(m, torch.nn.Linear):
+            h = torch.nn.functional.linear(h, table[f"net.{i}.weight"], table[f"net.{i}.bias"])
+        else:
+            h = m(h)
+    mean = torch.nn.functional.linear(h, table["mean.weight"], table["mean.bias"])
+    log_std = table["log_std"]
+    return torch.sum(-0.5 * (_LOG_2PI + 2.0 * log_std
+                             + (actions - mean) ** 2 / (torch.exp(log_std) + POLICY_EPS) ** 2), dim=1)
+
+
+# ------------------------------------------------------------------------------- batch cache
+class _Batch:
+    def __init__(self, states, actions, real_traj_lengths, num_traj, device, dtype):
+        lens = torch.as_tensor(real_traj_lengths).reshape(-1).to(torch.int64).cpu()
+        if lens.numel() != num_traj:
+            raise ValueError("num_traj does not match real_traj_lengths")
+        self.lens = lens.tolist()
+        s = torch.as_tensor(states)
+        a = torch.as_tensor(actions)
+        L = a.shape[1]
+        if all(l == L for l in self.lens):
+            s_flat = s[:, :L].reshape(-1, s.shape[-1])
+            a_flat = a.reshape(-1, a.shape[-1])
+        else:
+            s_flat = torch.cat([s[t, :l] for t, l in enumerate(self.lens)], 0)
+            a_flat = torch.cat([a[t, :l] for t, l in enumerate(self.lens)], 0)
+        self.states = s_flat.to(device=device, dtype=dtype).contiguous()
+        self.actions = a_flat.to(device=device, dtype=dtype).contiguous()
+        self.traj_off, self.n = traj_offsets(lens, device)
+        self.n_traj = int(num_traj)
+        self.action_dim = int(a.shape[-1])
+        self.behav_cache = None     # (param fingerprint, logp_b)
+
+
+_batches = {}
+_handles = {}
+
+
+def _cache_get(table, key_obj, extra, build):
+    key = (id(key_obj), extra)
+    hit = table.get(key)
+    if hit is not None and hit[0]() is key_obj:
+        return hit[1]
+    if len(table) > 8:
+        for k_ in [k_ for k_, v in table.items() if v[0]() is None]:
+            del table[k_]
+        while len(table) > 8:
+            table.pop(next(iter(table)))
+    val = build()
+    table[key] = (weakref.ref(key_obj), val)
+    return val
+
+
+def _get_batch(states, actions, real_traj_lengths, num_traj):
+    dev, dt = _device(), _config["compute_dtype"]
+    return _cache_get(_batches, states, (id(actions), dt, str(dev), getattr(states, "_version", 0)),
+                      lambda: _Batch(states, actions, real_traj_lengths, num_traj, dev, dt))
+
+
+def attach_handle(indices_cpu, handle):
+    """Remember the device-side search result that produced a CPU `indices` tensor (so the objective
+    does not have to re-upload it)."""
+    _handles[(id(indices_cpu), handle.k1)] = (weakref.ref(indices_cpu), handle)
+
+
+def _get_handle(distances, indices, k):
+    dev = _device()
+
+    def build():
+        idx = torch.as_tensor(indices).to(torch.int32).to(dev)
+        rk = torch.as_tensor(distances)[:, k].to(torch.float64).to(dev)
+        return SearchHandle(idx, rk, k + 1)
+
+    return _cache_get(_handles, indices, k + 1, build)
+
+
+def _fingerprint(policy):
+    return tuple((p.data_ptr(), p._version) for p in policy.parameters())
+
+
+def _burn_rng(batch, calls=2):
+    """Q7: every reference get_log_p call draws randn(len, A) from the global CPU generator
+    (policy.py:59), target first then behavioural, trajectory by trajectory (mepol.py:127-128)."""
+    if _config["burn_rng"]:
+        for l in batch.lens:
+            for _ in range(calls):
+                torch.randn((l, batch.action_dim), dtype=torch.float64)
+
+
+def _behav_logp(behavioral_policy, batch):
+    fp = _fingerprint(behavioral_policy)
+    if batch.behav_cache is not None and batch.behav_cache[0] == fp:
+        return batch.behav_cache[1]
+    with torch.no_grad():
+        params = mirror_params(behavioral_policy, batch.states.device, batch.states.dtype, False)
+        lb = gaussian_log_p(behavioral_policy, params, batch.states, batch.actions)
+    batch.behav_cache = (fp, lb)
+    return lb
+
+
+class _EntropyBridge(torch.autograd.Function):
+    """CPU parameters -> (entropy, kl_raw, n_bad) CPU scalars, everything in between on the GPU."""
+
+    @staticmethod
+    def forward(ctx, pack, *cpu_params):
+        target_policy, lb, batch, handle, k, ns, G, B, eps = pack
+        dev, dt = batch.states.device, batch.states.dtype
+        want_grad = any(ctx.needs_input_grad[1:])
+        gp = [p.detach().to(device=dev, dtype=dt).requires_grad_(want_grad) for p in cpu_params]
+        with torch.set_grad_enabled(want_grad):
+            lt = gaussian_log_p(target_policy, gp, batch.states, batch.actions)
+            H, kl_raw, n_bad = iw_entropy(lt, lb, handle, batch.traj_off, batch.n_traj, k, ns, G, B, eps)
+        ctx.gp, ctx.H = gp, (H if want_grad else None)
+        ctx.dtypes = [p.dtype for p in cpu_params]
+        out = torch.stack([H.detach(), kl_raw, n_bad]).cpu()
+        ent, klv, bad = out[0].clone(), out[1].clone(), out[2].clone()
+        ctx.mark_non_differentiable(klv, bad)
+        return ent, klv, bad
+
+    @staticmethod
+    def backward(ctx, g_ent, _g1, _g2):
+        grads = torch.autograd.grad(ctx.H, ctx.gp, g_ent.to(ctx.H.device, ctx.H.dtype), allow_unused=True)
+        outs = [None if g is None else g.to("cpu", dt_) for g, dt_ in zip(grads, ctx.dtypes)]
+        return (None, *outs)
+
+
+def _evaluate(behavioral_policy, target_policy, states, actions, num_traj, real_traj_lengths,
+              distances, indices, k, G, B, ns, eps):
+    batch = _get_batch(states, actions, real_traj_lengths, num_traj)
+    handle = _get_handle(distances, indices, k)
+    _burn_rng(batch)
+    lb = _behav_logp(behavioral_policy, batch)
+    pack = (target_policy, lb, batch, handle, k, ns, G, B, eps)
+    return _EntropyBridge.apply(pack, *list(target_policy.parameters()))
+
+
+# ------------------------------------------------------------------------------- reference surface
+def compute_importance_weights(behavioral_policy, target_policy, states, actions, num_traj, real_traj_lengths):
+    """mepol.py:114-139.  Returned for completeness (the objective kernels never materialise w on the
+    host): CPU float64 tensor [N] of self-normalised importance weights, no autograd."""
+    batch = _get_batch(states, actions, real_traj_lengths, num_traj)
+    _burn_rng(batch)
+    lb = _behav_logp(behavioral_policy, batch)
+    with torch.no_grad():
+        params = mirror_params(target_policy, batch.states.device, batch.states.dtype, False)
+        lt = gaussian_log_p(target_policy, params, batch.states, batch.actions)
+        n = batch.n
+        # run the forward kernels for their stabilised log-weights c, M = max c and S = sum exp(c - M);
+        # the neighbour inputs are dummies (identity index, unit radius)
+        idx = torch.arange(n, dtype=torch.int32, device=lt.device).reshape(n, 1).repeat(1, 2).contiguous()
+        rk = torch.ones(n, dtype=lt.dtype, device=lt.device)
+        c = torch.empty(n, dtype=lt.dtype, device=lt.device)
+        scal = torch.empty(8, dtype=torch.float64, device=lt.device)
+        ws = torch.empty(_lib.iw_workspace_bytes(n, batch.n_traj), dtype=torch.uint8, device=lt.device)
+        suffix = "f32" if lt.dtype == torch.float32 else "f64"
+        with torch.cuda.device(lt.device):
+            rc = getattr(_lib.load(), "mepol_iw_entropy_fwd_" + suffix)(
+                lt.data_ptr(), lb.to(lt.dtype).contiguous().data_ptr(), batch.traj_off.data_ptr(), batch.n_traj, n,
+                idx.data_ptr(), 2, rk.data_ptr(), 1, 0.0, 0.0, 0.0, c.data_ptr(), None,
+                scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(lt.device))
+        _lib.check(rc, "mepol_iw_entropy_fwd_" + suffix)
+        w = torch.exp(c.to(torch.float64) - scal[3]) / scal[4]
+    return w.cpu()
+
+
+def compute_entropy(behavioral_policy, target_policy, states, actions,
+                    num_traj, real_traj_lengths, distances, indices, k, G, B, ns, eps):
+    """mepol.py:142-154 -> 0-dim CPU float64 tensor (differentiable w.r.t. target_policy)."""
+    ent, _, _ = _evaluate(behavioral_policy, target_policy, states, actions, num_traj, real_traj_lengths,
+                          distances, indices, k, G, B, ns, eps)
+    return ent
+
+
+def compute_kl(behavioral_policy, target_policy, states, actions,
+               num_traj, real_traj_lengths, distances, indices, k, eps):
+    """mepol.py:157-174 -> (kl clamped at 0, numeric_error) as CPU tensors."""
+    with torch.no_grad():
+        _, kl_raw, _ = _evaluate(behavioral_policy, target_policy, states, actions, num_traj,
+                                 real_traj_lengths, distances, indices, k, None, 0.0, 1, eps)
+    numeric_error = torch.isinf(kl_raw) or torch.isnan(kl_raw)
+    kl = torch.max(torch.tensor(0.0, dtype=kl_raw.dtype), kl_raw)
+    return kl, numeric_error
+
+
+def policy_update(optimizer, behavioral_policy, target_policy, states, actions,
+                  num_traj, traj_len, distances, indices, k, G, B, ns, eps):
+    """mepol.py:268-281 (the argument called traj_len receives real_traj_lengths, :429-431)."""
+    optimizer.zero_grad()
+    loss = - compute_entropy(behavioral_policy, target_policy, states, actions,
+                             num_traj, traj_len, distances, indices, k, G, B, ns, eps)
+    numeric_error = torch.isinf(loss) or torch.isnan(loss)
+    loss.backward()
+    optimizer.step()
+    return loss, numeric_error
