@@ -72,6 +72,13 @@ int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float *q, int64_
                          int k1, int algo, int32_t *idx_out, double *dist_out, double *rk_out,
                          void *workspace, size_t workspace_bytes, int64_t *stats, void *stream);
 
+/* Test hook of the tensor-core pruner: writes the raw fp32 accumulator tile (scores
+ * ||y'||^2 - 2 x~.y~ of the first 256 query rows against the first 128 references) to out
+ * [256, 128] float32 (device).  Lets the tests check the tcgen05 contraction in isolation. */
+int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d,
+                          int k1, float *out, void *workspace, size_t workspace_bytes,
+                          void *stream);
+
 /* Host-buffer convenience form of the same call (what a ctypes/cgo-style binding of the reference
  * would use): x [n, d] float32 HOST, self-search, outputs HOST int64 / float64 [n, k1] exactly as
  * sklearn returns them.  Allocates, copies H2D, searches, copies D2H, frees, synchronises. */

@@ -211,6 +211,23 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     return MEPOL_OK;
 }
 
+// Bring-up / test hook of the tensor-core pruner: raw fp32 accumulator tile of the first 256 query
+// rows against the first 128 references (scores ||y'||^2 - 2 x~.y~), out [256, 128] float (device).
+extern "C" int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d, int k1,
+                                     float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    MEPOL_REQUIRE(ref && q && out && workspace, MEPOL_E_INVALID, "debug_tc_scores: null pointer");
+    KnnPlan p;
+    int rc = knn_make_plan(p, ref, n_ref, q, n_q, d, k1, MEPOL_KNN_TC, workspace);
+    if (rc != MEPOL_OK) return rc;
+    MEPOL_REQUIRE(workspace_bytes >= p.bytes, MEPOL_E_WORKSPACE, "debug_tc_scores: workspace %zu < %zu bytes",
+                  workspace_bytes, p.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    return launch_tc_dump(p, out, st);
+}
+
 __global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];

@@ -8,6 +8,15 @@ constexpr int kSimtThreads = 128;  // one query row (or two) per thread
 constexpr int kSimtTileRefs = 64;  // reference rows staged per shared-memory tile
 constexpr int kTcKPad = 32;        // bf16 operand width of the tensor-core pruner (d + 3 norm columns <= 32)
 
+// Element index (in bf16 units) of (row, column c) inside the tensor-core operand arrays: 128-row
+// tiles of 8 KB, each tile in UMMA canonical K-major no-swizzle order (8-row x 16-byte core
+// matrices of 128 B; next core matrix along K at +128 B, next 8-row group at +512 B).
+__host__ __device__ inline size_t tc_elem_index(int64_t row, int c) {
+    const size_t tile = (size_t)(row >> 7);
+    const int r = (int)(row & 127);
+    return tile * 4096 + (size_t)(((r >> 3) * 4 + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7));
+}
+
 // indices into the float "glob" array produced by the pack kernels (stored as uint bits, atomicMax)
 enum { G_AMAX = 0, G_DELTA_MAX = 1, G_ATILDE_MAX = 2, G_COUNT = 4 };
 
@@ -47,6 +56,7 @@ int launch_prune_simt(const KnnPlan &p, cudaStream_t st);
 // knn_tc.cu
 bool tc_supported(int d, int k1);
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st);
+int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st);
 // knn_rerank.cu
 int launch_rerank(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
                   double *dist_out, double *rk_out, cudaStream_t st);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128)
                 dl2 += (hv - v) * (hv - v);
                 nt2 += hv * hv;
                 __nv_bfloat16 st = is_ref ? __float2bfloat16(-2.0f * __bfloat162float(hb)) : hb;  // x2 exact
-                xb[row * kTcKPad + c] = __bfloat16_as_ushort(st);
+                xb[tc_elem_index(row, c)] = __bfloat16_as_ushort(st);
             }
         }
         if (o)
@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(128)
             delta_up = __double2float_ru(sqrt(dl2) * (1.0 + 1e-12));
             atilde_up = __double2float_ru(sqrt(nt2) * (1.0 + 1e-12));
             if (delta) delta[row] = delta_up;
-            uint16_t *ob = xb + row * kTcKPad;
             if (is_ref) {
                 // ||y'||^2 split over three bf16 columns: hi + mid + lo reproduces it to ~2^-24
                 __nv_bfloat16 h = __double2bfloat16(n2);
@@ -110,22 +109,21 @@ __global__ void __launch_bounds__(128)
                 __nv_bfloat16 m = __double2bfloat16(r1);
                 double r2 = r1 - (double)__bfloat162float(m);
                 __nv_bfloat16 l = __double2bfloat16(r2);
-                ob[d] = __bfloat16_as_ushort(h);
-                ob[d + 1] = __bfloat16_as_ushort(m);
-                ob[d + 2] = __bfloat16_as_ushort(l);
+                xb[tc_elem_index(row, d)] = __bfloat16_as_ushort(h);
+                xb[tc_elem_index(row, d + 1)] = __bfloat16_as_ushort(m);
+                xb[tc_elem_index(row, d + 2)] = __bfloat16_as_ushort(l);
             } else {
                 const uint16_t one = __bfloat16_as_ushort(__float2bfloat16(1.0f));
-                ob[d] = one;
-                ob[d + 1] = one;
-                ob[d + 2] = one;
+                xb[tc_elem_index(row, d)] = one;
+                xb[tc_elem_index(row, d + 1)] = one;
+                xb[tc_elem_index(row, d + 2)] = one;
             }
-            for (int c = d + 3; c < kTcKPad; ++c) ob[c] = 0;
+            for (int c = d + 3; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
         }
     } else if (row < n_pad && xb) {
         // padding rows of the tensor-core operand: references get a huge norm so they never win
-        uint16_t *ob = xb + row * kTcKPad;
-        for (int c = 0; c < kTcKPad; ++c) ob[c] = 0;
-        if (is_ref) ob[d] = __bfloat16_as_ushort(__float2bfloat16(3.0e38f));
+        for (int c = 0; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
+        if (is_ref) xb[tc_elem_index(row, d)] = __bfloat16_as_ushort(__float2bfloat16(3.0e38f));
     }
     if (is_ref) {
         // max over the fitted set (bit patterns of non-negative floats order like unsigned ints)
