@@ -84,6 +84,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rows_per_thread = 1;
         p.rows_per_cta = 256;
         p.n_split = 1;
+        p.cap = 32;   // kTcCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
         p.n_ref_pad = (n_ref + 127) / 128 * 128;
         p.n_q_pad = (n_q + 255) / 256 * 256;
     }
@@ -111,6 +112,11 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
     p.cand = c.take<int32_t>((size_t)n_q * p.n_split * p.cap);
     p.cand_cnt = c.take<int32_t>((size_t)n_q * p.n_split);
     p.flag = c.take<unsigned char>((size_t)n_q);
+    p.fb_max_rows = (int)(n_q < 4096 ? n_q : 4096);
+    p.fb_list = c.take<int32_t>((size_t)p.fb_max_rows);
+    p.fb_count = c.take<int>(4);
+    p.fb_part_d = c.take<double>((size_t)p.fb_max_rows * fallback_chunks_for(k1) * k1);
+    p.fb_part_i = c.take<int32_t>((size_t)p.fb_max_rows * fallback_chunks_for(k1) * k1);
     p.bytes = c.bytes();
     return MEPOL_OK;
 }
@@ -203,6 +209,10 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
     if (rc != MEPOL_OK) return rc;
+    {
+        const char *em = getenv("MEPOL_TC_EPI_MODE");   // bring-up timing aid: results are invalid, stop here
+        if (em && atoi(em) != 0) return MEPOL_OK;
+    }
     if ((rc = launch_rerank(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
     if ((rc = launch_exact_fallback(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
     if (stats)

@@ -42,6 +42,11 @@ struct KnnPlan {
     uint16_t *rb, *qb;
     float *q_delta;
     int64_t n_ref_pad, n_q_pad;
+    // parallel exact fallback scratch
+    int fb_max_rows;
+    int32_t *fb_list, *fb_part_i;
+    int *fb_count;
+    double *fb_part_d;
     size_t bytes;
 };
 
@@ -60,6 +65,7 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st);
 // knn_rerank.cu
 int launch_rerank(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
                   double *dist_out, double *rk_out, cudaStream_t st);
+int fallback_chunks_for(int k1);
 int launch_exact_fallback(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
                           double *dist_out, double *rk_out, cudaStream_t st);
 

@@ -37,7 +37,9 @@ constexpr int kTcRows = 256;
 constexpr int kTcTileRefs = 128;
 constexpr int kTcStages = 6;
 constexpr int kTcTileBytes = 128 * kTcKPad * 2;  // 8192
-constexpr int kTcCap = 32;
+constexpr int kTcSoftCap = 32;                   // candidates a row may carry between column groups / emit
+constexpr int kTcCap = 64;                       // physical buffer entries per row (soft cap + one 32-column group)
+constexpr int kTcBufStride = kTcCap + 1;         // row-major, padded: conflict-free both per-lane and per-row
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
 constexpr int kTcTmemCols = 512;
@@ -45,11 +47,11 @@ constexpr int kTcTmemCols = 512;
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + 2 * kTcTileBytes;
 constexpr int kSmemBufV = kSmemB + kTcStages * kTcTileBytes;
-constexpr int kSmemBufI = kSmemBufV + kTcCap * kTcRows * 4;
-constexpr int kSmemBar = kSmemBufI + kTcCap * kTcRows * 4;
-constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kSmemBufI = kSmemBufV + kTcBufStride * kTcRows * 4;
+constexpr int kSmemBar = (kSmemBufI + kTcBufStride * kTcRows * 4 + 127) / 128 * 128;
+constexpr int kSmemTotal = kSmemBar + 512;
 
-bool tc_supported(int d, int k1) { return d + 3 <= kTcKPad && 2 * k1 + 8 <= kTcCap; }
+bool tc_supported(int d, int k1) { return d + 3 <= kTcKPad && 2 * k1 + 8 <= kTcSoftCap; }
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
                         uint32_t lbo_bytes, uint32_t sbo_bytes, int32_t *__restrict__ cand,
                         int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
-                        unsigned long long *__restrict__ stats, float *__restrict__ dump) {
+                        unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,11 +202,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_arrive_expect_tx(bar_a_full, 2 * kTcTileBytes);
                 bulk_g2s(sbase + kSmemA, qb + (size_t)rblk * kTcRows * kTcKPad, 2 * kTcTileBytes, bar_a_full);
                 const int tiles = kDump ? 1 : n_ref_tiles;
+                // every CTA starts its sweep over the reference tiles at a different offset so that
+                // the 148 SMs do not hammer the same L2 lines at the same moment
+                const int rot = kDump ? 0 : (int)(((long long)blockIdx.x * n_ref_tiles) / gridDim.x);
                 for (int j = 0; j < tiles; ++j, ++it) {
+                    int jt = j + rot;
+                    if (jt >= n_ref_tiles) jt -= n_ref_tiles;
                     const uint32_t st = it % kTcStages;
                     mbar_wait(bar_empty + 8 * st, ((it / kTcStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * st, kTcTileBytes);
-                    bulk_g2s(sbase + kSmemB + st * kTcTileBytes, rb + (size_t)j * kTcTileRefs * kTcKPad, kTcTileBytes,
+                    bulk_g2s(sbase + kSmemB + st * kTcTileBytes, rb + (size_t)jt * kTcTileRefs * kTcKPad, kTcTileBytes,
                              bar_full + 8 * st);
                 }
             }
@@ -246,68 +253,166 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int t = warp >> 2;                       // accumulator (row tile) of this warp
         const int row_in_tile = (warp & 3) * 32 + lane;
         const int rloc = t * 128 + row_in_tile;        // row inside the CTA's 256-row block
+        const int warp_row0 = rloc - lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        RowBuf buf_row{reinterpret_cast<float *>(smem + kSmemBufV) + rloc,
-                       reinterpret_cast<int *>(smem + kSmemBufI) + rloc, kTcRows};
+        float *bufv = reinterpret_cast<float *>(smem + kSmemBufV);
+        int *bufi = reinterpret_cast<int *>(smem + kSmemBufI);
+        const int my_base = rloc * kTcBufStride;
         const float A = glob[G_AMAX], D = glob[G_DELTA_MAX];
+        const float INF = __int_as_float(0x7f800000);
         uint32_t acc_it = 0;
         unsigned n_compactions = 0;
         unsigned long long n_cand = 0;
+
+        // Cooperative compaction of lane L's buffer (up to 64 entries, two per lane): the k1-th
+        // smallest is found by rank counting over 64 shuffles, tau tightens to t + band, survivors
+        // are re-packed with ballot prefixes.  A few hundred warp instructions, no serial scan.
+        auto coop_compact = [&](int L, int &cnt, float &tau, float band, bool &ovf) {
+            const int base = (warp_row0 + L) * kTcBufStride;
+            const int n = __shfl_sync(0xffffffffu, cnt, L);
+            const float tau_L = __shfl_sync(0xffffffffu, tau, L);
+            const float band_L = __shfl_sync(0xffffffffu, band, L);
+            const bool ok0 = lane < n, ok1 = lane + 32 < n;
+            const float v0 = ok0 ? bufv[base + lane] : INF;
+            const float v1 = ok1 ? bufv[base + 32 + lane] : INF;
+            const int i0 = ok0 ? bufi[base + lane] : -1;
+            const int i1 = ok1 ? bufi[base + 32 + lane] : -1;
+            int c0 = 0, c1 = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float o0 = __shfl_sync(0xffffffffu, v0, j);
+                const float o1 = __shfl_sync(0xffffffffu, v1, j);
+                c0 += (o0 <= v0 ? 1 : 0) + (o1 <= v0 ? 1 : 0);
+                c1 += (o0 <= v1 ? 1 : 0) + (o1 <= v1 ? 1 : 0);
+            }
+            float tk = fminf((c0 >= k1) ? v0 : INF, (c1 >= k1) ? v1 : INF);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffffu, tk, o));
+            const float nt = fminf(tau_L, tk + band_L);
+            const bool k0 = ok0 && v0 <= nt, k1b = ok1 && v1 <= nt;
+            const unsigned m0 = __ballot_sync(0xffffffffu, k0);
+            const unsigned m1 = __ballot_sync(0xffffffffu, k1b);
+            const unsigned lt = (1u << lane) - 1u;
+            const int p0 = __popc(m0 & lt), p1 = __popc(m0) + __popc(m1 & lt);
+            __syncwarp();
+            if (k0) {
+                bufv[base + p0] = v0;
+                bufi[base + p0] = i0;
+            }
+            if (k1b) {
+                bufv[base + p1] = v1;
+                bufi[base + p1] = i1;
+            }
+            __syncwarp();
+            if (lane == L) {
+                tau = nt;
+                cnt = __popc(m0) + __popc(m1);
+                ++n_compactions;
+                if (cnt > kTcSoftCap) {                // the band alone overfills the buffer: exact fallback row
+                    ovf = true;
+                    cnt = 0;
+                    tau = -INF;
+                }
+            }
+        };
+
         for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x) {
             const int row = rblk * kTcRows + rloc;
             const bool live = row < n_q;
-            float tau = __int_as_float(0x7f800000);
+            float tau = live ? INF : -INF;             // padding rows never collect anything
             const float band = live ? tc_band(q_anorm[row], q_delta[row], A, D) : 0.f;
             int cnt = 0;
             bool ovf = false;
             const int tiles = kDump ? 1 : n_ref_tiles;
+            const int rot = kDump ? 0 : (int)(((long long)blockIdx.x * n_ref_tiles) / gridDim.x);
             for (int j = 0; j < tiles; ++j, ++acc_it) {
+                int jt = j + rot;
+                if (jt >= n_ref_tiles) jt -= n_ref_tiles;
                 const uint32_t buf = acc_it & 1;
                 mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + lane_base + buf * 256 + t * 128;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    float v[32];
-                    tc_ld32(tbase + c * 32, v);
+                // pull the thread's whole 128-column row into registers and hand the TMEM buffer
+                // back to the MMA issuer at once: the filter below overlaps the next tile's MMA
+                float v[4][32];
+                __syncwarp();
+                if (epi_mode != 2) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tc_ld32(tbase + c * 32, v[c]);
                     tc_wait_ld();
-                    if (kDump) {
-                        if (rblk == 0)
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) dump[(size_t)rloc * kTcTileRefs + c * 32 + jj] = v[jj];
-                        continue;
-                    }
-                    float m[11];
-#pragma unroll
-                    for (int g = 0; g < 10; ++g) m[g] = fmin3(v[3 * g], v[3 * g + 1], v[3 * g + 2]);
-                    m[10] = fminf(v[30], v[31]);
-                    const float m0 = fmin3(m[0], m[1], m[2]), m1 = fmin3(m[3], m[4], m[5]);
-                    const float m2 = fmin3(m[6], m[7], m[8]), m3 = fminf(m[9], m[10]);
-                    const float mm = fminf(fmin3(m0, m1, m2), m3);
-                    if (mm < tau) {
-                        const int ref0 = j * kTcTileRefs + c * 32;
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            if (v[jj] < tau && ref0 + jj < n_ref)
-                                rowbuf_push(buf_row, cnt, tau, v[jj], ref0 + jj, k1, band, kTcCap, ovf, n_compactions);
-                        }
-                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-            }
-            if (!kDump && live) {
-                if (!ovf && cnt > k1) rowbuf_compact(buf_row, cnt, tau, k1, band, kTcCap, ovf);
-                if (ovf) {
-                    flag[row] = 1;
-                    cand_cnt[row] = 0;
-                } else {
-                    cand_cnt[row] = cnt;
-                    int32_t *dst = cand + (size_t)row * kTcCap;
-                    for (int e = 0; e < cnt; ++e) dst[e] = buf_row.ix[e * kTcRows];
-                    n_cand += cnt;
+                if (epi_mode != 0) continue;          // bring-up timing modes: no filter
+                if (kDump) {
+                    if (rblk == 0)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) dump[(size_t)rloc * kTcTileRefs + c * 32 + jj] = v[c][jj];
+                    continue;
                 }
+                float gm[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float m[11];
+#pragma unroll
+                    for (int g = 0; g < 10; ++g) m[g] = fmin3(v[c][3 * g], v[c][3 * g + 1], v[c][3 * g + 2]);
+                    m[10] = fminf(v[c][30], v[c][31]);
+                    const float m0 = fmin3(m[0], m[1], m[2]), m1 = fmin3(m[3], m[4], m[5]);
+                    const float m2 = fmin3(m[6], m[7], m[8]), m3 = fminf(m[9], m[10]);
+                    gm[c] = fminf(fmin3(m0, m1, m2), m3);
+                }
+                const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+                if (__any_sync(0xffffffffu, mm < tau)) {
+                    // warp-uniform slow path.  Invariant: cnt <= kTcSoftCap (32) on entry to a
+                    // 32-column group, a group appends at most 32, the buffer holds 64.
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (!__any_sync(0xffffffffu, gm[c] < tau)) continue;
+                        const int ref0 = jt * kTcTileRefs + c * 32;
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            if (v[c][jj] < tau && ref0 + jj < n_ref) {
+                                bufv[my_base + cnt] = v[c][jj];
+                                bufi[my_base + cnt] = ref0 + jj;
+                                ++cnt;
+                            }
+                        }
+                        unsigned full = __ballot_sync(0xffffffffu, cnt > kTcSoftCap);
+                        while (full) {
+                            const int L = __ffs(full) - 1;
+                            full &= full - 1;
+                            coop_compact(L, cnt, tau, band, ovf);
+                        }
+                    }
+                }
+            }
+            if (!kDump) {
+                // final tightening + coalesced write-out of every row of the warp
+                unsigned need = __ballot_sync(0xffffffffu, live && !ovf && cnt > k1);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    coop_compact(L, cnt, tau, band, ovf);
+                }
+                if (live) {
+                    if (ovf) {
+                        flag[row] = 1;
+                        cand_cnt[row] = 0;
+                    } else {
+                        cand_cnt[row] = cnt;
+                        n_cand += cnt;
+                    }
+                }
+                __syncwarp();
+                for (int L = 0; L < 32; ++L) {
+                    const int nL = __shfl_sync(0xffffffffu, (live && !ovf) ? cnt : 0, L);
+                    const int rowL = rblk * kTcRows + warp_row0 + L;
+                    if (lane < nL) cand[(size_t)rowL * kTcSoftCap + lane] = bufi[(warp_row0 + L) * kTcBufStride + lane];
+                }
+                __syncwarp();
             }
         }
         if (!kDump && stats) {
@@ -348,9 +453,11 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     const int n_ref_tiles = (int)(p.n_ref_pad / kTcTileRefs);
     int grid = device_sm_count();
     if (grid > n_row_blocks) grid = n_row_blocks;
+    const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up aid only (results invalid when set)
+    const int epi_mode = em ? atoi(em) : 0;
     kern<<<grid, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
                                                n_row_blocks, p.glob, p.k1, lbo, sbo, p.cand, p.cand_cnt, p.flag,
-                                               p.stats, nullptr);
+                                               p.stats, nullptr, epi_mode);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
@@ -362,7 +469,7 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
     auto kern = knn_prune_tc_kernel<true>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
-                                            p.k1, lbo, sbo, p.cand, p.cand_cnt, p.flag, nullptr, dump);
+                                            p.k1, lbo, sbo, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

@@ -84,7 +84,22 @@ def knn(n):
     return same
 
 
+def time_only(n):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, 29)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    mepol_b200.knn_device(xt, 5, algo=_lib.KNN_TC)
+    _lib.profile_enable(True)
+    for _ in range(3):
+        mepol_b200.knn_device(xt, 5, algo=_lib.KNN_TC)
+    torch.cuda.synchronize()
+    print("mode=%s N=%d prune_ms=%s" % (os.environ.get("MEPOL_TC_EPI_MODE", "0"), n, _lib.profile_read()))
+    return True
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "time":
+        sys.exit(0 if time_only(int(sys.argv[2])) else 1)
     if sys.argv[1] == "dump":
         sys.exit(0 if dump() else 1)
     else:
