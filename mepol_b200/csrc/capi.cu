@@ -238,6 +238,9 @@ extern "C" int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const floa
     return launch_tc_dump(p, out, st);
 }
 
+namespace mepol { int tc_read_timestamps(long long *host_out); }
+extern "C" int mepol_debug_tc_timestamps(long long *host_out) { return mepol::tc_read_timestamps(host_out); }
+
 __global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];

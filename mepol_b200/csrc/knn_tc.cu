@@ -9,18 +9,23 @@
 //   D = A . B^T  = ||y'||^2 - 2 x~.y~   (fp32 accumulator in TMEM; the row-constant ||x'||^2 is
 //                                         dropped, it does not change a row's ranking)
 //
-// so the accumulator IS the ranking key and the epilogue does no arithmetic on it: one
-// tcgen05.ld (32 columns of the thread's own row), a 3-input-min tree (FMNMX3), one compare with
-// the row's pruning threshold, and a rare slow path that appends survivors to the row's candidate
-// buffer (knn_internal.cuh).  Exactness comes from the proven error band (see tc_band) and the
-// fp64 re-rank, never from bf16.
+// so the accumulator IS the ranking key and the epilogue does no arithmetic on it: tcgen05.ld of
+// the thread's own 128-column row, a 3-input-min tree (FMNMX3), one compare with the row's pruning
+// threshold, and a rare slow path that appends survivors to the row's candidate buffer.
+// Exactness comes from the proven error band (tc_band) and the fp64 re-rank, never from bf16.
 //
 // CTA = 256 query rows (two M=128 accumulators) x a stream of 128-reference B tiles.
-//   warp 8      bulk-copy producer (cp.async.bulk -> smem, mbarrier complete_tx), 6-stage ring
-//   warp 9      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M128 N128 K16 x2)
+//   warp 8      bulk-copy producer (cp.async.bulk -> smem, mbarrier complete_tx), 4-stage ring
+//   warp 9      TMEM allocator + tcgen05.mma issuer (cta_group::1, M128 N128 K16, 4 per tile)
 //   warps 0-7   epilogue: warp w owns TMEM lanes 32*(w%4).. of accumulator w/4, one row per thread
-// TMEM: 2 buffers x 2 accumulators x 128 columns = 512 columns (all of it) -> MMA of tile j+1
-// overlaps the epilogue of tile j.  Persistent grid (one CTA per SM) over row blocks.
+// TMEM: 2 buffers x 2 accumulators x 128 columns = 512 columns (all of it).  The epilogue pulls a
+// tile into registers and releases the TMEM buffer before filtering, so the MMA of tile j+1/j+2
+// overlaps the filter of tile j.  Persistent grid (one CTA per SM) over row blocks.
+//
+// Measured on B200 (profiles/): with K = 32 the tensor pipe needs only 256 cycles per tile, so the
+// kernel is bound by fixed per-tile latencies (mbarrier try_wait ~220 cycles even when already
+// complete, tcgen05.ld ~300, tcgen05.mma issue ~70 each), not by the MMA; the structure below
+// minimises the number of serial long-latency operations per tile in every role.
 //
 // Operand tiles are pre-arranged in global memory by knn_prep.cu in the UMMA canonical K-major
 // no-swizzle order (8x16-byte core matrices, 128 B each): a 128-row x 32-col tile is 8 KB
@@ -35,20 +40,23 @@ namespace mepol {
 
 constexpr int kTcRows = 256;
 constexpr int kTcTileRefs = 128;
-constexpr int kTcStages = 6;
+constexpr int kTcStages = 4;
 constexpr int kTcTileBytes = 128 * kTcKPad * 2;  // 8192
 constexpr int kTcSoftCap = 32;                   // candidates a row may carry between column groups / emit
 constexpr int kTcCap = 64;                       // physical buffer entries per row (soft cap + one 32-column group)
 constexpr int kTcBufStride = kTcCap + 1;         // row-major, padded: conflict-free both per-lane and per-row
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcThreads = (kTcEpiWarps + 4) * 32;   // 8 epilogue warps + producer + issuer + 2 idle (whole warpgroup for setmaxnreg)
+constexpr int kTcEpiRegs = 216;                        // setmaxnreg budget of the epilogue warpgroups
+constexpr int kTcAuxRegs = 40;                         //   ... and of the producer/issuer warpgroup
 constexpr int kTcTmemCols = 512;
 
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + 2 * kTcTileBytes;
 constexpr int kSmemBufV = kSmemB + kTcStages * kTcTileBytes;
 constexpr int kSmemBufI = kSmemBufV + kTcBufStride * kTcRows * 4;
-constexpr int kSmemBar = (kSmemBufI + kTcBufStride * kTcRows * 4 + 127) / 128 * 128;
+constexpr int kSmemStage = kSmemBufI + kTcBufStride * kTcRows * 4;            // per-warp 32x33 transpose tiles
+constexpr int kSmemBar = (kSmemStage + kTcEpiWarps * 32 * 33 * 4 + 127) / 128 * 128;
 constexpr int kSmemTotal = kSmemBar + 512;
 
 bool tc_supported(int d, int k1) { return d + 3 <= kTcKPad && 2 * k1 + 8 <= kTcSoftCap; }
@@ -70,6 +78,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a hardware time slice)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -149,35 +169,31 @@ __device__ __forceinline__ float tc_band(float a, float dx, float A, float D) {
     return 2.0f * e + 1e-37f;
 }
 
-template <bool kDump>
+template <bool kDump, int K1>
 __global__ void __launch_bounds__(kTcThreads, 1)
     knn_prune_tc_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
                         const float *__restrict__ q_delta, int n_q, const uint16_t *__restrict__ rb, int n_ref,
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
-                        uint32_t lbo_bytes, uint32_t sbo_bytes, int32_t *__restrict__ cand,
-                        int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
+                        int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
                         unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barrier slots
-    const uint32_t bar_full = sbase + kSmemBar;                    // [stages]
-    const uint32_t bar_empty = bar_full + 8 * kTcStages;           // [stages]
-    const uint32_t bar_acc_full = bar_empty + 8 * kTcStages;       // [2]
-    const uint32_t bar_acc_empty = bar_acc_full + 16;              // [2]
+    // barrier slots.  done[s]: the MMAs that read B stage s have retired (tcgen05.commit): the stage
+    // may be refilled AND the accumulators they wrote are ready -- one commit serves both consumers.
+    const uint32_t bar_full = sbase + kSmemBar;                    // [stages] producer -> issuer
+    const uint32_t bar_done = bar_full + 8 * kTcStages;            // [stages] issuer -> producer + epilogue
+    const uint32_t bar_acc_empty = bar_done + 8 * kTcStages;       // [2]      epilogue -> issuer
     const uint32_t bar_a_full = bar_acc_empty + 16;
     const uint32_t bar_a_empty = bar_a_full + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (2 * kTcStages + 6));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (2 * kTcStages + 4));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_acc_full + 8 * b, 1);
-            mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps);
-        }
+        for (int b = 0; b < 2; ++b) mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps);
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -192,6 +208,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int tiles = kDump ? 1 : n_ref_tiles;
+    // Register re-distribution at warpgroup granularity (setmaxnreg): the epilogue keeps a whole
+    // 128-column row in registers, the producer / issuer / idle warps need almost none.
+    if (warp >= kTcEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcAuxRegs));
 
     if (warp == kTcEpiWarps) {
         // ===================== bulk-copy producer =====================
@@ -201,15 +221,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_wait(bar_a_empty, (rbi & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_a_full, 2 * kTcTileBytes);
                 bulk_g2s(sbase + kSmemA, qb + (size_t)rblk * kTcRows * kTcKPad, 2 * kTcTileBytes, bar_a_full);
-                const int tiles = kDump ? 1 : n_ref_tiles;
-                // every CTA starts its sweep over the reference tiles at a different offset so that
-                // the 148 SMs do not hammer the same L2 lines at the same moment
-                const int rot = kDump ? 0 : (int)(((long long)blockIdx.x * n_ref_tiles) / gridDim.x);
+                // The sweep over the reference tiles starts at the row block's own position: CTAs do
+                // not hit the same L2 lines at the same moment, and in a self-search the rows' own
+                // neighbourhood (same trajectory) is seen first, which tightens tau early.
+                const int rot = kDump ? 0 : (epi_mode == 4 ? 0 : (rblk * 2) % n_ref_tiles);
                 for (int j = 0; j < tiles; ++j, ++it) {
                     int jt = j + rot;
                     if (jt >= n_ref_tiles) jt -= n_ref_tiles;
                     const uint32_t st = it % kTcStages;
-                    mbar_wait(bar_empty + 8 * st, ((it / kTcStages) & 1) ^ 1);
+                    mbar_wait(bar_done + 8 * st, ((it / kTcStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * st, kTcTileBytes);
                     bulk_g2s(sbase + kSmemB + st * kTcTileBytes, rb + (size_t)jt * kTcTileRefs * kTcKPad, kTcTileBytes,
                              bar_full + 8 * st);
@@ -218,38 +238,48 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
     } else if (warp == kTcEpiWarps + 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, rbi = 0, acc_it = 0;
-            for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x, ++rbi) {
-                mbar_wait(bar_a_full, rbi & 1);
-                const int tiles = kDump ? 1 : n_ref_tiles;
-                for (int j = 0; j < tiles; ++j, ++it, ++acc_it) {
-                    const uint32_t st = it % kTcStages;
-                    const uint32_t buf = acc_it & 1;
-                    mbar_wait(bar_acc_empty + 8 * buf, ((acc_it >> 1) & 1) ^ 1);
-                    mbar_wait(bar_full + 8 * st, (it / kTcStages) & 1);
-                    tc_fence_after();
-                    const uint32_t b_addr = sbase + kSmemB + st * kTcTileBytes;
+        // The whole warp runs the loop so that the two barrier waits of a tile are ONE warp-wide
+        // try_wait (lane 1 polls full[stage], the other lanes poll acc_empty[buffer]); lane 0 issues.
+        uint64_t a_desc[2][2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+                a_desc[t][ks] = umma_desc(sbase + kSmemA + t * kTcTileBytes + ks * 256, 128, 512);
+        const uint64_t b_desc0 = umma_desc(sbase + kSmemB, 128, 512);
+        uint32_t it = 0, rbi = 0;
+        for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x, ++rbi) {
+            mbar_wait(bar_a_full, rbi & 1);
+            for (int j = 0; j < tiles; ++j, ++it) {
+                const uint32_t st = it % kTcStages;
+                const uint32_t buf = it & 1;
+                const uint32_t my_bar = (lane == 1) ? bar_full + 8 * st : bar_acc_empty + 8 * buf;
+                const uint32_t my_par = (lane == 1) ? ((it / kTcStages) & 1) : (((it >> 1) & 1) ^ 1);
+                uint32_t spins = 0;
+                while (!__all_sync(0xffffffffu, mbar_try_wait(my_bar, my_par))) {
+                    if (++spins > (1u << 25)) __trap();
+                }
+                tc_fence_after();
+                if (lane == 0) {
+                    // one K=16 step = two 16-byte k-chunks = 256 bytes further along K
+                    const uint64_t bd0 = b_desc0 + (uint64_t)((st * kTcTileBytes) >> 4);
+                    const uint64_t bd1 = bd0 + (256 >> 4);
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
-                        const uint32_t a_addr = sbase + kSmemA + t * kTcTileBytes;
                         const uint32_t d_addr = tmem_base + buf * 256 + t * 128;
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            // one K=16 step = two 16-byte k-chunks = 256 bytes further along K
-                            const uint64_t ad = umma_desc(a_addr + ks * 256, lbo_bytes, sbo_bytes);
-                            const uint64_t bd = umma_desc(b_addr + ks * 256, lbo_bytes, sbo_bytes);
-                            tc_mma_bf16(d_addr, ad, bd, kTcIdesc, ks);
-                        }
+                        tc_mma_bf16(d_addr, a_desc[t][0], bd0, kTcIdesc, 0);
+                        tc_mma_bf16(d_addr, a_desc[t][1], bd1, kTcIdesc, 1);
                     }
-                    tc_commit(bar_empty + 8 * st);        // smem stage reusable once these MMAs retire
-                    tc_commit(bar_acc_full + 8 * buf);    // accumulators ready for the epilogue
+                    tc_commit(bar_done + 8 * st);
                 }
-                tc_commit(bar_a_empty);                   // query tiles reusable
+                __syncwarp();
             }
+            if (lane == 0) tc_commit(bar_a_empty);   // query tiles reusable once every MMA of the block retired
+            __syncwarp();
         }
-    } else {
+    } else if (warp < kTcEpiWarps) {
         // ===================== epilogue: one query row per thread =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
         const int t = warp >> 2;                       // accumulator (row tile) of this warp
         const int row_in_tile = (warp & 3) * 32 + lane;
         const int rloc = t * 128 + row_in_tile;        // row inside the CTA's 256-row block
@@ -260,35 +290,53 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int my_base = rloc * kTcBufStride;
         const float A = glob[G_AMAX], D = glob[G_DELTA_MAX];
         const float INF = __int_as_float(0x7f800000);
-        uint32_t acc_it = 0;
+        uint32_t it = 0;
         unsigned n_compactions = 0;
         unsigned long long n_cand = 0;
+        bool next_ready = false;
 
-        // Cooperative compaction of lane L's buffer (up to 64 entries, two per lane): the k1-th
-        // smallest is found by rank counting over 64 shuffles, tau tightens to t + band, survivors
-        // are re-packed with ballot prefixes.  A few hundred warp instructions, no serial scan.
+        float *stg = reinterpret_cast<float *>(smem + kSmemStage) + warp * (32 * 33);   // per-warp transpose tile
+        // Running k1 smallest scores of the thread's row, ascending (K1 > 0 only): tau follows the
+        // CURRENT k1-th smallest + band instead of waiting for the next compaction, which halves the
+        // number of survivors that have to be appended.  Inserting +inf is a no-op.
+        float topk[K1 > 0 ? K1 : 1];
+        auto topk_insert = [&](float x) {
+#pragma unroll
+            for (int i = 0; i < (K1 > 0 ? K1 : 0); ++i) {
+                const float lo = fminf(topk[i], x);
+                x = fmaxf(topk[i], x);
+                topk[i] = lo;
+            }
+        };
+
+        // Cooperative compaction of lane L's buffer (up to 64 entries, two per lane).  The k1-th
+        // smallest comes from the running list (K1 > 0) or from rank counting over 64 shuffles
+        // (generic k1); tau tightens to t + band, survivors are re-packed with ballot prefixes.
         auto coop_compact = [&](int L, int &cnt, float &tau, float band, bool &ovf) {
             const int base = (warp_row0 + L) * kTcBufStride;
             const int n = __shfl_sync(0xffffffffu, cnt, L);
             const float tau_L = __shfl_sync(0xffffffffu, tau, L);
-            const float band_L = __shfl_sync(0xffffffffu, band, L);
             const bool ok0 = lane < n, ok1 = lane + 32 < n;
             const float v0 = ok0 ? bufv[base + lane] : INF;
             const float v1 = ok1 ? bufv[base + 32 + lane] : INF;
             const int i0 = ok0 ? bufi[base + lane] : -1;
             const int i1 = ok1 ? bufi[base + 32 + lane] : -1;
-            int c0 = 0, c1 = 0;
+            float nt = tau_L;
+            if (K1 == 0) {
+                const float band_L = __shfl_sync(0xffffffffu, band, L);
+                int c0 = 0, c1 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float o0 = __shfl_sync(0xffffffffu, v0, j);
-                const float o1 = __shfl_sync(0xffffffffu, v1, j);
-                c0 += (o0 <= v0 ? 1 : 0) + (o1 <= v0 ? 1 : 0);
-                c1 += (o0 <= v1 ? 1 : 0) + (o1 <= v1 ? 1 : 0);
+                for (int j = 0; j < 32; ++j) {
+                    const float o0 = __shfl_sync(0xffffffffu, v0, j);
+                    const float o1 = __shfl_sync(0xffffffffu, v1, j);
+                    c0 += (o0 <= v0 ? 1 : 0) + (o1 <= v0 ? 1 : 0);
+                    c1 += (o0 <= v1 ? 1 : 0) + (o1 <= v1 ? 1 : 0);
+                }
+                float tk = fminf((c0 >= k1) ? v0 : INF, (c1 >= k1) ? v1 : INF);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffffu, tk, o));
+                nt = fminf(tau_L, tk + band_L);
             }
-            float tk = fminf((c0 >= k1) ? v0 : INF, (c1 >= k1) ? v1 : INF);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffffu, tk, o));
-            const float nt = fminf(tau_L, tk + band_L);
             const bool k0 = ok0 && v0 <= nt, k1b = ok1 && v1 <= nt;
             const unsigned m0 = __ballot_sync(0xffffffffu, k0);
             const unsigned m1 = __ballot_sync(0xffffffffu, k1b);
@@ -323,28 +371,34 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const float band = live ? tc_band(q_anorm[row], q_delta[row], A, D) : 0.f;
             int cnt = 0;
             bool ovf = false;
-            const int tiles = kDump ? 1 : n_ref_tiles;
-            const int rot = kDump ? 0 : (int)(((long long)blockIdx.x * n_ref_tiles) / gridDim.x);
-            for (int j = 0; j < tiles; ++j, ++acc_it) {
+#pragma unroll
+            for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
+            const int rot = kDump ? 0 : (rblk * 2) % n_ref_tiles;
+            for (int j = 0; j < tiles; ++j, ++it) {
                 int jt = j + rot;
                 if (jt >= n_ref_tiles) jt -= n_ref_tiles;
-                const uint32_t buf = acc_it & 1;
-                mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1);
+                const uint32_t buf = it & 1;
+                const uint32_t st = it % kTcStages;
+                if (!next_ready) mbar_wait(bar_done + 8 * st, (it / kTcStages) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + lane_base + buf * 256 + t * 128;
                 // pull the thread's whole 128-column row into registers and hand the TMEM buffer
-                // back to the MMA issuer at once: the filter below overlaps the next tile's MMA
+                // back to the MMA issuer at once: the filter below overlaps the next tiles' MMAs
                 float v[4][32];
-                __syncwarp();
+                __syncwarp();                          // .sync.aligned TMEM ops need a converged warp
                 if (epi_mode != 2) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tc_ld32(tbase + c * 32, v[c]);
-                    tc_wait_ld();
                 }
+                {   // probe the next tile's barrier while the TMEM loads are in flight
+                    const uint32_t st1 = (it + 1) % kTcStages;
+                    next_ready = mbar_test_wait(bar_done + 8 * st1, ((it + 1) / kTcStages) & 1);
+                }
+                if (epi_mode != 2) tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-                if (epi_mode != 0) continue;          // bring-up timing modes: no filter
+                if (epi_mode == 1 || epi_mode == 2) continue;   // bring-up timing modes: no filter
                 if (kDump) {
                     if (rblk == 0)
 #pragma unroll
@@ -366,26 +420,49 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
                 const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
                 if (__any_sync(0xffffffffu, mm < tau)) {
-                    // warp-uniform slow path.  Invariant: cnt <= kTcSoftCap (32) on entry to a
-                    // 32-column group, a group appends at most 32, the buffer holds 64.
+                    // Warp-uniform, branch-light slow path.  The 32x32 group (32 rows x 32 columns)
+                    // is transposed through shared memory so that, for every row with a survivor, the
+                    // 32 lanes test its 32 columns at once and append all survivors with one ballot.
+                    // Invariant: cnt <= kTcSoftCap (32) on entry, a group appends <= 32, buffer = 64.
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        if (!__any_sync(0xffffffffu, gm[c] < tau)) continue;
+                        unsigned hit_lanes = __ballot_sync(0xffffffffu, gm[c] < tau);
+                        if (hit_lanes == 0) continue;
                         const int ref0 = jt * kTcTileRefs + c * 32;
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            if (v[c][jj] < tau && ref0 + jj < n_ref) {
-                                bufv[my_base + cnt] = v[c][jj];
-                                bufi[my_base + cnt] = ref0 + jj;
-                                ++cnt;
+                        for (int jj = 0; jj < 32; ++jj) stg[lane * 33 + jj] = v[c][jj];
+                        __syncwarp();
+                        while (hit_lanes) {
+                            const int L = __ffs(hit_lanes) - 1;
+                            hit_lanes &= hit_lanes - 1;
+                            const float tau_L = __shfl_sync(0xffffffffu, tau, L);
+                            const int cnt_L = __shfl_sync(0xffffffffu, cnt, L);
+                            const int base_L = (warp_row0 + L) * kTcBufStride;
+                            const float x = stg[L * 33 + lane];
+                            const bool h = x < tau_L && ref0 + lane < n_ref;
+                            unsigned hm = __ballot_sync(0xffffffffu, h);
+                            const int n_new = __popc(hm);
+                            if (h) {
+                                const int pos = cnt_L + __popc(hm & ((1u << lane) - 1u));
+                                bufv[base_L + pos] = x;
+                                bufi[base_L + pos] = ref0 + lane;
+                            }
+                            if (lane == L) cnt += n_new;
+                            if (K1 > 0) {
+                                while (hm) {
+                                    const int src = __ffs(hm) - 1;
+                                    hm &= hm - 1;
+                                    const float xv = __shfl_sync(0xffffffffu, x, src);
+                                    topk_insert(lane == L ? xv : INF);
+                                }
+                                tau = fminf(tau, topk[K1 - 1] + band);
+                            }
+                            if (cnt_L + n_new > kTcSoftCap) {
+                                __syncwarp();
+                                coop_compact(L, cnt, tau, band, ovf);
                             }
                         }
-                        unsigned full = __ballot_sync(0xffffffffu, cnt > kTcSoftCap);
-                        while (full) {
-                            const int L = __ffs(full) - 1;
-                            full &= full - 1;
-                            coop_compact(L, cnt, tau, band, ovf);
-                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -434,44 +511,36 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 }
 
-static void tc_layout_params(uint32_t &lbo, uint32_t &sbo) {
-    lbo = 128;
-    sbo = 512;
-    const char *sw = getenv("MEPOL_TC_SWAP_LBO_SBO");   // bring-up aid only
-    if (sw && sw[0] == '1') {
-        lbo = 512;
-        sbo = 128;
-    }
-}
-
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
-    uint32_t lbo, sbo;
-    tc_layout_params(lbo, sbo);
-    auto kern = knn_prune_tc_kernel<false>;
+    // k+1 = 5 (every shipped MEPOL config but GridWorld) gets the register-resident running top-k1
+    auto kern = p.k1 == 5 ? knn_prune_tc_kernel<false, 5> : knn_prune_tc_kernel<false, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     const int n_row_blocks = (int)(p.n_q_pad / kTcRows);
     const int n_ref_tiles = (int)(p.n_ref_pad / kTcTileRefs);
     int grid = device_sm_count();
     if (grid > n_row_blocks) grid = n_row_blocks;
-    const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up aid only (results invalid when set)
+    const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up timing aid only (results invalid when set)
     const int epi_mode = em ? atoi(em) : 0;
     kern<<<grid, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
-                                               n_row_blocks, p.glob, p.k1, lbo, sbo, p.cand, p.cand_cnt, p.flag,
-                                               p.stats, nullptr, epi_mode);
+                                               n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, nullptr,
+                                               epi_mode);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
 
-// Bring-up / test hook: raw accumulator tile (first 256 query rows x first 128 references).
+// Test hook: raw accumulator tile (first 256 query rows x first 128 references).
 int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
-    uint32_t lbo, sbo;
-    tc_layout_params(lbo, sbo);
-    auto kern = knn_prune_tc_kernel<true>;
+    auto kern = knn_prune_tc_kernel<true, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
-                                            p.k1, lbo, sbo, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0);
+                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
+}
+
+int tc_read_timestamps(long long *) {
+    set_error("timestamp instrumentation is not compiled into this build");
+    return MEPOL_E_UNSUPPORTED;
 }
 
 }  // namespace mepol

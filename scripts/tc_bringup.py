@@ -94,6 +94,13 @@ def time_only(n):
         mepol_b200.knn_device(xt, 5, algo=_lib.KNN_TC)
     torch.cuda.synchronize()
     print("mode=%s N=%d prune_ms=%s" % (os.environ.get("MEPOL_TC_EPI_MODE", "0"), n, _lib.profile_read()))
+    if int(os.environ.get("MEPOL_TC_EPI_MODE", "0")) >= 10:
+        ts = np.zeros((6, 16), dtype=np.int64)
+        _lib.check(_lib.load().mepol_debug_tc_timestamps(ts.ctypes.data), "ts")
+        t0 = ts[0, 0]
+        names = ["mma_ready", "mma_committed", "epi0_wake", "epi0_loaded", "epi7_wake", "prod_issued"]
+        for i, nm in enumerate(names):
+            print("%-14s" % nm, " ".join("%6d" % (v - t0) for v in ts[i]))
     return True
 
 
