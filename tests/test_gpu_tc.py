@@ -1,0 +1,78 @@
+"""GPU tests specific to the tcgen05 pruner: the raw tensor-core score tile against a float64
+emulation of the bf16 operands, and bit-identity of the full search with the SIMT path (both are
+exact, so they must agree on every index and every distance)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mepol_b200
+from mepol_b200 import _lib
+
+
+def _expected_scores(x, nq=256, nr=128):
+    """Mirror of knn_prep.cu's packing: centre with the float32-rounded mean, round to bf16, split
+    ||y'||^2 over three bf16 terms; D = sum(n_hi, n_mid, n_lo) - 2 x~.y~ in float64."""
+    xd = torch.from_numpy(x).double()
+    mean = (xd.sum(0) / x.shape[0]).float().double()
+    xc = xd - mean
+    xb = xc.float().to(torch.bfloat16).double()
+    n2 = (xc * xc).sum(1)
+    h = n2.float().to(torch.bfloat16).double()
+    m = (n2 - h).float().to(torch.bfloat16).double()
+    l = (n2 - h - m).float().to(torch.bfloat16).double()
+    return ((h + m + l)[:nr][None, :] - 2.0 * (xb[:nq] @ xb[:nr].T)).numpy()
+
+
+@pytest.mark.parametrize("d", [29, 24, 7, 2])
+def test_tensor_core_score_tile(d):
+    rng = np.random.default_rng(d)
+    n = 1024
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    out = torch.full((256, 128), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(_lib.knn_workspace_bytes(n, n, d, 5, _lib.KNN_TC), dtype=torch.uint8, device="cuda")
+    rc = _lib.load().mepol_debug_tc_scores(xt.data_ptr(), n, xt.data_ptr(), n, d, 5, out.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mepol_debug_tc_scores")
+    got = out.cpu().numpy().astype(np.float64)
+    exp = _expected_scores(x)
+    assert not np.isnan(got).any()
+    # fp32 accumulation of 32 exact bf16 products: a few ulp of the largest term
+    assert np.max(np.abs(got - exp)) < 1e-4 * max(1.0, np.abs(exp).max())
+
+
+@pytest.mark.parametrize("n,d,k1", [(70000, 29, 5), (33000, 29, 2), (20000, 16, 5), (9000, 29, 12), (40000, 7, 5)])
+def test_tc_and_simt_searches_are_bit_identical(n, d, k1):
+    rng = np.random.default_rng(n)
+    x = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+    a = mepol_b200.knn_device(x, k1, algo=_lib.KNN_SIMT)
+    b = mepol_b200.knn_device(x, k1, algo=_lib.KNN_TC)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+    assert torch.equal(a.rk, b.rk)
+
+
+def test_tc_rejects_unsupported_shapes():
+    x = torch.zeros((5000, 40), device="cuda")
+    with pytest.raises(_lib.MepolError):
+        mepol_b200.knn_device(x, 5, algo=_lib.KNN_TC)         # d + 3 > 32
+    x = torch.zeros((5000, 8), device="cuda")
+    with pytest.raises(_lib.MepolError):
+        mepol_b200.knn_device(x, 30, algo=_lib.KNN_TC)        # k1 too large for the 32-entry soft cap
+    res = mepol_b200.knn_device(torch.randn((5000, 40), device="cuda"), 5)   # AUTO falls back to SIMT
+    assert res.indices.shape == (5000, 5)
+
+
+def test_tc_offset_clustered_data_uses_band_and_fallback_correctly():
+    """Tight clusters far from the origin: after centring the bf16 band is wide relative to the
+    neighbour gaps, so many rows overflow into the exact fallback -- results must still be exact."""
+    from oracle import knn_oracle
+    rng = np.random.default_rng(8)
+    centers = rng.standard_normal((20, 29)) * 30
+    x = (centers[rng.integers(0, 20, 12000)] + 0.01 * rng.standard_normal((12000, 29))).astype(np.float32)
+    ref_d, ref_i = knn_oracle.knn_c(x, 5, mode="kd_tree")
+    res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), 5, algo=_lib.KNN_TC)
+    np.testing.assert_array_equal(res.indices.cpu().numpy(), ref_i)
+    np.testing.assert_allclose(res.distances.cpu().numpy(), ref_d, rtol=1e-12)
