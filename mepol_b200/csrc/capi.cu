@@ -84,7 +84,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rows_per_thread = 1;
         p.rows_per_cta = 256;
         p.n_split = 1;
-        p.cap = 32;   // kTcCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
+        p.cap = 32;   // kTcSoftCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
         p.n_ref_pad = (n_ref + 127) / 128 * 128;
         p.n_q_pad = (n_q + 255) / 256 * 256;
     }
