@@ -368,7 +368,8 @@ def run_ours(args):
                           f"{rows} query rows vs all {n} fitted rows ({ts:.1f} s, scaled x{n / rows:.1f}) + float64 numpy "
                           f"port of compute_entropy/compute_kl/backward on all {n} states ({ti:.2f} s)")}
 
-    launches_per_step = 6 + 6 + 3   # search (mean x2, pack, prune, rerank, fallback) + rev-CSR (6) + IW (scan, gather, bwd)
+    # search: col mean x2, pack x2, prune, re-rank, fallback list/partial/merge/serial = 11; rev-CSR 6; IW scan, gather, bwd = 3
+    launches_per_step = 11 + 6 + 3
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "bf16",
