@@ -79,10 +79,6 @@ int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const float *q, int64
                           int k1, float *out, void *workspace, size_t workspace_bytes,
                           void *stream);
 
-/* Bring-up instrumentation: SM-clock timestamps [6][16] recorded by CTA 0 of the last tensor-core
- * pruning launch when MEPOL_TC_EPI_MODE >= 10 (results of that launch are invalid). */
-int mepol_debug_tc_timestamps(long long *host_out);
-
 /* Host-buffer convenience form of the same call (what a ctypes/cgo-style binding of the reference
  * would use): x [n, d] float32 HOST, self-search, outputs HOST int64 / float64 [n, k1] exactly as
  * sklearn returns them.  Allocates, copies H2D, searches, copies D2H, frees, synchronises. */

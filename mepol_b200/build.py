@@ -18,7 +18,7 @@ SOURCES = ["capi.cu", "knn_prep.cu", "knn_simt.cu", "knn_tc.cu", "knn_rerank.cu"
 NVCC = os.environ.get("MEPOL_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-         "-ccbin", "/usr/bin/g++"]
+         "-ccbin", "/usr/bin/g++"] + os.environ.get("MEPOL_NVCC_EXTRA", "").split()
 
 
 def _deps():

@@ -209,10 +209,12 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
     if (rc != MEPOL_OK) return rc;
+#ifdef MEPOL_BRINGUP
     {
         const char *em = getenv("MEPOL_TC_EPI_MODE");   // bring-up timing aid: results are invalid, stop here
         if (em && atoi(em) != 0) return MEPOL_OK;
     }
+#endif
     if ((rc = launch_rerank(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
     if ((rc = launch_exact_fallback(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
     if (stats)
@@ -237,9 +239,6 @@ extern "C" int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const floa
     if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     return launch_tc_dump(p, out, st);
 }
-
-namespace mepol { int tc_read_timestamps(long long *host_out); }
-extern "C" int mepol_debug_tc_timestamps(long long *host_out) { return mepol::tc_read_timestamps(host_out); }
 
 __global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -304,6 +304,136 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 }
 
+// ---------------------------------------------------------------- warp-per-trajectory variants
+// With thousands of short trajectories (the N=1M benchmark has 2098 of length 500) a CTA per
+// trajectory spends its time in __syncthreads; here one warp scans one trajectory in 32-element
+// chunks with shuffles only, four chunks of loads in flight, and keeps a running (max, sum exp)
+// pair per lane so the trajectory is read exactly once.
+constexpr int kWarpScanWarps = 8;
+
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpScanWarps * 32)
+    iw_scan_warp_kernel(const T *__restrict__ lt, const T *__restrict__ lb, const int32_t *__restrict__ traj_off,
+                        int n_traj, T *__restrict__ c_out, double *__restrict__ traj_max,
+                        double *__restrict__ traj_sum, unsigned *__restrict__ counters, double *__restrict__ scal) {
+    __shared__ double s_warp[32];
+    __shared__ double s_bcast;
+    __shared__ unsigned s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * kWarpScanWarps + warp;
+    const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
+    if (t < n_traj) {
+        const int lo = traj_off[t], hi = traj_off[t + 1];
+        double carry = 0.0, m = NEG_INF, ssum = 0.0;
+        for (int base = lo; base < hi; base += 128) {
+            double dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = base + 32 * u + lane;
+                dv[u] = j < hi ? (double)lt[j] - (double)lb[j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = base + 32 * u + lane;
+                const double incl = warp_inclusive_scan(dv[u], lane) + carry;
+                carry = __shfl_sync(0xffffffffu, incl, 31);
+                if (j < hi) {
+                    const T stored = (T)incl;
+                    c_out[j] = stored;
+                    const double cv = (double)stored;
+                    if (cv > m) {           // online (max, sum exp(c - max)); NaN falls through to the sum
+                        ssum = ssum * exp(m - cv) + 1.0;
+                        m = cv;
+                    } else {
+                        ssum += exp(cv - m);
+                    }
+                }
+            }
+        }
+        // fold the 32 (max, sum) pairs
+        const double wm = warp_max(m);
+        const double part = warp_sum(m == NEG_INF ? 0.0 : ssum * exp(m - wm));
+        if (lane == 0) {
+            traj_max[t] = wm;
+            traj_sum[t] = (hi > lo) ? part : 0.0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_ticket = atomicAdd(counters + 0, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // last CTA: fold per-trajectory (max, sum) pairs in fixed order
+    __threadfence();
+    double gm = NEG_INF;
+    for (int i = threadIdx.x; i < n_traj; i += blockDim.x) gm = fmax(gm, ((volatile double *)traj_max)[i]);
+    gm = block_reduce_max(gm, s_warp);
+    if (threadIdx.x == 0) s_bcast = gm;
+    __syncthreads();
+    gm = s_bcast;
+    double gs = 0.0;
+    for (int i = threadIdx.x; i < n_traj; i += blockDim.x) {
+        const double tm = ((volatile double *)traj_max)[i];
+        const double ts = ((volatile double *)traj_sum)[i];
+        if (ts != 0.0) gs += ts * exp(tm - gm);
+    }
+    gs = block_reduce_sum(gs, s_warp);
+    if (threadIdx.x == 0) {
+        scal[3] = gm;
+        scal[4] = gs;
+        scal[6] = (gm > 709.782712893384 || gm < -745.1332191019412) ? 1.0 : 0.0;   // see iw_scan_kernel
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpScanWarps * 32)
+    iw_bwd_warp_kernel(const T *__restrict__ c, const T *__restrict__ gW, const double *__restrict__ scal,
+                       const int32_t *__restrict__ traj_off, int n_traj, const int32_t *__restrict__ rowptr,
+                       const int32_t *__restrict__ col, const double *__restrict__ grad_H, T *__restrict__ grad_lt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * kWarpScanWarps + warp;
+    if (t >= n_traj) return;
+    const int lo = traj_off[t], hi = traj_off[t + 1];
+    const double M = scal[3], S = scal[4], s = scal[2];
+    const double gH = grad_H[0];
+    const T Mt = (T)M;
+    double carry = 0.0;
+    // walk backwards: position p = 0 is the LAST step of the trajectory
+    for (int base = 0; base < hi - lo; base += 128) {
+        double gc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = hi - 1 - (base + 32 * u + lane);
+            gc[u] = 0.0;
+            if (j >= lo) {
+                double gw = 0.0;
+                const int e0 = rowptr[j], e1 = rowptr[j + 1];
+                for (int e = e0; e < e1; ++e) gw += (double)gW[col[e]];
+                const double w = (double)RowMath<T>::exp_(c[j] - Mt) / S;
+                gc[u] = w * (gw - s);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = hi - 1 - (base + 32 * u + lane);
+            const double incl = warp_inclusive_scan(gc[u], lane) + carry;
+            carry = __shfl_sync(0xffffffffu, incl, 31);
+            if (j >= lo) grad_lt[j] = (T)(gH * incl);
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------- K4 reverse CSR
 constexpr int kCsrThreads = 256;
 
@@ -407,6 +537,7 @@ __global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, 
     }
 }
 
+constexpr int kWarpPathMinTraj = 512;   // below this a CTA per trajectory has more parallelism
 constexpr int kCsrItems = 8;
 static int csr_blocks_for(int64_t n) { return (int)((n + (int64_t)kCsrThreads * kCsrItems - 1) / ((int64_t)kCsrThreads * kCsrItems)); }
 
@@ -474,8 +605,12 @@ static int iw_fwd_impl(const T *lt, const T *lb, const int32_t *traj_off, int64_
                   workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MEPOL_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, 4 * sizeof(unsigned), st));
-    iw_scan_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(lt, lb, traj_off, (int)n_traj, c, w.traj_max,
-                                                            w.traj_sum, w.counters, scal);
+    if (n_traj >= kWarpPathMinTraj)
+        iw_scan_warp_kernel<T><<<(int)((n_traj + kWarpScanWarps - 1) / kWarpScanWarps), kWarpScanWarps * 32, 0, st>>>(
+            lt, lb, traj_off, (int)n_traj, c, w.traj_max, w.traj_sum, w.counters, scal);
+    else
+        iw_scan_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(lt, lb, traj_off, (int)n_traj, c, w.traj_max,
+                                                                w.traj_sum, w.counters, scal);
     iw_gather_kernel<T><<<gather_blocks_for(n), kGatherThreads, 0, st>>>(
         c, idx, k1, (int)n, rk, ns, log_G, B, eps, gW, w.blk_part, w.counters, scal);
     MEPOL_CUDA_CHECK(cudaGetLastError());
@@ -490,7 +625,11 @@ static int iw_bwd_impl(const T *c, const T *gW, const double *scal, const int32_
                   "iw_entropy_bwd: null pointer");
     MEPOL_REQUIRE(n > 0 && n_traj > 0, MEPOL_E_INVALID, "iw_entropy_bwd: bad sizes");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    iw_bwd_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(c, gW, scal, traj_off, rowptr, col, grad_H, grad_lt);
+    if (n_traj >= kWarpPathMinTraj)
+        iw_bwd_warp_kernel<T><<<(int)((n_traj + kWarpScanWarps - 1) / kWarpScanWarps), kWarpScanWarps * 32, 0, st>>>(
+            c, gW, scal, traj_off, (int)n_traj, rowptr, col, grad_H, grad_lt);
+    else
+        iw_bwd_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(c, gW, scal, traj_off, rowptr, col, grad_H, grad_lt);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

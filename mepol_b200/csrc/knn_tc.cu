@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 // The sweep over the reference tiles starts at the row block's own position: CTAs do
                 // not hit the same L2 lines at the same moment, and in a self-search the rows' own
                 // neighbourhood (same trajectory) is seen first, which tightens tau early.
-                const int rot = kDump ? 0 : (epi_mode == 4 ? 0 : (rblk * 2) % n_ref_tiles);
+                const int rot = kDump ? 0 : (rblk * 2) % n_ref_tiles;
                 for (int j = 0; j < tiles; ++j, ++it) {
                     int jt = j + rot;
                     if (jt >= n_ref_tiles) jt -= n_ref_tiles;
@@ -406,8 +406,12 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     const int n_ref_tiles = (int)(p.n_ref_pad / kTcTileRefs);
     int grid = device_sm_count();
     if (grid > n_row_blocks) grid = n_row_blocks;
-    const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up timing aid only (results invalid when set)
-    const int epi_mode = em ? atoi(em) : 0;
+#ifdef MEPOL_BRINGUP
+    const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up timing aid (results invalid when set):
+    const int epi_mode = em ? atoi(em) : 0;              // 1 = TMEM loads only, 2 = barriers + MMA only
+#else
+    const int epi_mode = 0;
+#endif
     kern<<<grid, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
                                                n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, nullptr,
                                                epi_mode);
@@ -423,11 +427,6 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
                                             p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
-}
-
-int tc_read_timestamps(long long *) {
-    set_error("timestamp instrumentation is not compiled into this build");
-    return MEPOL_E_UNSUPPORTED;
 }
 
 }  // namespace mepol

@@ -1,4 +1,5 @@
-"""Bring-up diagnostics for the tcgen05 pruner (run on the B200 box):
+"""Bring-up diagnostics for the tcgen05 pruner (run on the B200 box; the MEPOL_TC_EPI_MODE timing
+switch needs a library built with -DMEPOL_BRINGUP: MEPOL_NVCC_EXTRA=-DMEPOL_BRINGUP python -m mepol_b200.build --force):
    python scripts/tc_bringup.py dump      # raw accumulator tile vs a numpy emulation of the bf16 operands
    python scripts/tc_bringup.py knn N     # TC search vs SIMT search (indices must be identical), timing
 """
@@ -94,13 +95,6 @@ def time_only(n):
         mepol_b200.knn_device(xt, 5, algo=_lib.KNN_TC)
     torch.cuda.synchronize()
     print("mode=%s N=%d prune_ms=%s" % (os.environ.get("MEPOL_TC_EPI_MODE", "0"), n, _lib.profile_read()))
-    if int(os.environ.get("MEPOL_TC_EPI_MODE", "0")) >= 10:
-        ts = np.zeros((6, 16), dtype=np.int64)
-        _lib.check(_lib.load().mepol_debug_tc_timestamps(ts.ctypes.data), "ts")
-        t0 = ts[0, 0]
-        names = ["mma_ready", "mma_committed", "epi0_wake", "epi0_loaded", "epi7_wake", "prod_issued"]
-        for i, nm in enumerate(names):
-            print("%-14s" % nm, " ".join("%6d" % (v - t0) for v in ts[i]))
     return True
 
 

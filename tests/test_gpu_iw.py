@@ -145,6 +145,38 @@ def test_large_synthetic_batch_matches_oracle(dtype, tol):
     assert H2.item() == H.item() and torch.equal(ltt2.grad, ltt.grad)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-5)])
+def test_many_short_ragged_trajectories_use_the_warp_kernels(dtype, tol):
+    """>= 512 trajectories switches the scan / backward to the warp-per-trajectory kernels; ragged
+    lengths (incl. length 1 and > 128) exercise their chunking."""
+    rng = np.random.default_rng(23)
+    T, k, ns = 900, 4, 7
+    lens = rng.integers(1, 300, T)
+    lens[:3] = [1, 129, 257]
+    n = int(lens.sum())
+    idx = rng.integers(0, n, (n, k + 1)).astype(np.int32)
+    idx[:, 0] = np.arange(n)
+    rk = rng.uniform(0.1, 2.0, n)
+    lt = rng.normal(0, 0.03, n)
+    lb = rng.normal(0, 0.03, n)
+    G = math.gamma(ns / 2 + 1)
+    B = math.log(k) - 1.2561176684318
+    dist = np.zeros((n, k + 1)); dist[:, k] = rk
+    H_ref = O.entropy(lt, lb, lens, dist, idx, k, G, B, ns, 0.0)
+    kl_ref, _ = O.kl(lt, lb, lens, idx, k, 0.0)
+    g_ref = O.entropy_grad_logp(lt, lb, lens, dist, idx, k, G, ns, 0.0)
+    dev = torch.device("cuda")
+    h = E.SearchHandle(torch.from_numpy(idx).to(dev), torch.from_numpy(rk).to(dev), k + 1)
+    off, _ = mepol_b200.traj_offsets(lens, dev)
+    ltt = torch.tensor(lt, dtype=dtype, device=dev, requires_grad=True)
+    H, kl_raw, n_bad = mepol_b200.iw_entropy(ltt, torch.tensor(lb, dtype=dtype, device=dev), h, off, T, k, ns, G, B, 0.0)
+    H.backward()
+    np.testing.assert_allclose(H.item(), H_ref, rtol=tol)
+    np.testing.assert_allclose(max(kl_raw.item(), 0.0), kl_ref, rtol=10 * tol, atol=1e-7 if dtype == torch.float32 else 1e-13)
+    got = ltt.grad.double().cpu().numpy()
+    np.testing.assert_allclose(got / np.abs(g_ref).max(), g_ref / np.abs(g_ref).max(), rtol=0, atol=tol)
+
+
 def test_numeric_error_flags():
     """exp overflow (float64 range) and zero radius ('knn aliasing') give nan/inf exactly where the
     reference does (mepol.py:168, :276, :485)."""
