@@ -273,10 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 // back to the MMA issuer at once: the filter below overlaps the next tiles' MMAs
                 float v[4][32];
                 __syncwarp();                          // .sync.aligned TMEM ops need a converged warp
-                if (epi_mode != 2) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) tc_ld32(tbase + c * 32, v[c]);
-                }
+                if (epi_mode != 2) tc_ld128(tbase, v);
                 {   // probe the next tile's barrier while the TMEM loads are in flight
                     const uint32_t st1 = (it + 1) % kTcStages;
                     next_ready = mbar_test_wait(bar_done + 8 * st1, ((it + 1) / kTcStages) & 1);
@@ -316,6 +313,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         unsigned hit_lanes = __ballot_sync(0xffffffffu, gm[c] < tau);
                         if (hit_lanes == 0) continue;
                         const int ref0 = jt * kTcTileRefs + c * 32;
+                        if (__popc(hit_lanes) > 10) {
+                            // Dense case (the first tiles of a row block, before tau has tightened): most
+                            // rows have survivors, so every lane appends its own straight from registers
+                            // (predicated, no per-row loop); tau is refreshed once per group.
+                            const float tau0 = tau;
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) {
+                                const bool h = v[c][jj] < tau0 && ref0 + jj < n_ref;
+                                if (h) {
+                                    bufv[my_base + cnt] = v[c][jj];
+                                    bufi[my_base + cnt] = ref0 + jj;
+                                    ++cnt;
+                                }
+                                if (K1 > 0) topk_insert(h ? v[c][jj] : INF);
+                            }
+                            if (K1 > 0) tau = fminf(tau, topk[K1 - 1] + band);
+                            unsigned full = __ballot_sync(0xffffffffu, cnt > kTcSoftCap);
+                            while (full) {
+                                const int L = __ffs(full) - 1;
+                                full &= full - 1;
+                                coop_compact(L, cnt, tau, band, ovf);
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) stg[lane * 33 + jj] = v[c][jj];
                         __syncwarp();
