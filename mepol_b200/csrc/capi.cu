@@ -49,7 +49,11 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
                   k1, (long long)n_ref);
     MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC, MEPOL_E_INVALID,
                   "knn: unknown algo %d", algo);
-    if (algo == MEPOL_KNN_AUTO) algo = (tc_supported(d, k1) && n_ref >= 4096) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
+    // AUTO: tensor cores pay off for wide particles and large batches; for d < 16 (the regime where
+    // sklearn itself switches to a kd-tree, neighbors/_base.py:615-626) the bf16 band is too coarse
+    // for the tiny neighbour radii and the fp32 SIMT pruner is both exact-band-tight and cheap.
+    if (algo == MEPOL_KNN_AUTO)
+        algo = (tc_supported(d, k1) && n_ref >= 4096 && d >= 16) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
     if (algo == MEPOL_KNN_TC && !tc_supported(d, k1)) {
         set_error("knn: tensor-core pruner does not support d=%d k1=%d", d, k1);
         return MEPOL_E_UNSUPPORTED;
@@ -75,11 +79,6 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         if (max_split > ref_tiles / 4) max_split = ref_tiles / 4;
         if (max_split < 1) max_split = 1;
         p.n_split = (int)(want < 1 ? 1 : (want > max_split ? max_split : want));
-        // a query slice of the fitted matrix can reuse the packed reference rows
-        if (ref && q && q >= ref && q + n_q * d <= ref + n_ref * d && ((q - ref) % d) == 0) {
-            p.q_is_ref = true;
-            p.q_row0 = (q - ref) / d;
-        }
     } else {
         p.rows_per_thread = 1;
         p.rows_per_cta = 256;
@@ -88,6 +87,11 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.n_ref_pad = (n_ref + 127) / 128 * 128;
         p.n_q_pad = (n_q + 255) / 256 * 256;
     }
+    // a query slice of the fitted matrix can reuse the packed fp32 reference rows
+    if (ref && q && q >= ref && q + n_q * d <= ref + n_ref * d && ((q - ref) % d) == 0) {
+        p.q_is_ref = true;
+        p.q_row0 = (q - ref) / d;
+    }
     Carver c(ws);
     p.mean_partial = c.take<double>((size_t)p.mean_blocks * MEPOL_MAX_DIM);
     p.mean = c.take<double>(MEPOL_MAX_DIM);
@@ -95,16 +99,16 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
     p.stats = c.take<unsigned long long>(MEPOL_KNN_NSTATS);
     p.r_anorm = c.take<float>((size_t)n_ref);
     p.q_anorm = c.take<float>((size_t)n_q);
-    if (algo == MEPOL_KNN_SIMT) {
-        p.rs = c.take<float>((size_t)n_ref * p.dpad);
-        p.r_nrm = c.take<float>((size_t)n_ref);
-        if (p.q_is_ref) {
-            p.qs = ws ? p.rs + p.q_row0 * p.dpad : nullptr;
-            p.q_anorm = ws ? p.r_anorm + p.q_row0 : nullptr;
-        } else {
-            p.qs = c.take<float>((size_t)n_q * p.dpad);
-        }
+    // fp32 operands: the SIMT pruner's input, and the rescue pass's input behind the TC pruner
+    p.rs = c.take<float>((size_t)n_ref * p.dpad);
+    p.r_nrm = c.take<float>((size_t)n_ref);
+    if (p.q_is_ref) {
+        p.qs = ws ? p.rs + p.q_row0 * p.dpad : nullptr;
+        if (algo == MEPOL_KNN_SIMT) p.q_anorm = ws ? p.r_anorm + p.q_row0 : nullptr;
     } else {
+        p.qs = c.take<float>((size_t)n_q * p.dpad);
+    }
+    if (algo == MEPOL_KNN_TC) {
         p.rb = c.take<uint16_t>((size_t)p.n_ref_pad * kTcKPad);
         p.qb = c.take<uint16_t>((size_t)p.n_q_pad * kTcKPad);
         p.q_delta = c.take<float>((size_t)n_q);
@@ -201,7 +205,7 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     MEPOL_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * MEPOL_KNN_NSTATS, st));
     if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
     if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
-    if (!p.q_is_ref && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     prof_record(0, st);
     if (p.algo == MEPOL_KNN_TC)
         rc = launch_prune_tc(p, st);
@@ -209,6 +213,8 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
     if (rc != MEPOL_OK) return rc;
+    // rows whose bf16 band overflowed are re-pruned with the fp32 band before the exact fallback
+    if (p.algo == MEPOL_KNN_TC && (rc = launch_rescue_simt(p, st)) != MEPOL_OK) return rc;
 #ifdef MEPOL_BRINGUP
     {
         const char *em = getenv("MEPOL_TC_EPI_MODE");   // bring-up timing aid: results are invalid, stop here

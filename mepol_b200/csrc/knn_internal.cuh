@@ -58,6 +58,7 @@ int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cu
 int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, cudaStream_t st);
 // knn_simt.cu
 int launch_prune_simt(const KnnPlan &p, cudaStream_t st);
+int launch_rescue_simt(const KnnPlan &p, cudaStream_t st);
 // knn_tc.cu
 bool tc_supported(int d, int k1);
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st);

@@ -144,8 +144,11 @@ int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref,
     if (!tc) n_pad = n;
     const int64_t rows = n_pad > n ? n_pad : n;
     const int blocks = (int)((rows + 127) / 128);
+    // fp32 operands are produced in both modes (SIMT search / rescue pass); query rows that alias
+    // the fitted matrix reuse the reference rows
+    float *xs = is_ref ? p.rs : (p.q_is_ref ? nullptr : p.qs);
     pack_rows_kernel<<<blocks, 128, 0, st>>>(
-        x, n, n_pad, d, p.dpad, p.mean, tc ? nullptr : (is_ref ? p.rs : p.qs), is_ref ? p.r_nrm : nullptr,
+        x, n, n_pad, d, p.dpad, p.mean, xs, is_ref ? p.r_nrm : nullptr,
         is_ref ? p.r_anorm : p.q_anorm, tc ? (is_ref ? p.rb : p.qb) : nullptr,
         tc ? (is_ref ? nullptr : p.q_delta) : nullptr, p.glob, is_ref ? 1 : 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
