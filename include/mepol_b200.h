@@ -63,7 +63,7 @@ int mepol_profile_read(float *ms_out, int max_n, int *n_out);
  * rk_out   [n_q] float64, optional (may be NULL) -- dist_out[:, k1-1] as a contiguous column, the
  *       only distance the objective consumes (mepol.py:150).
  * stats    optional DEVICE int64[MEPOL_KNN_NSTATS]: {candidates re-ranked, rows sent to the exact
- *       fallback, buffer compactions, 0...}.
+ *       fallback, buffer compactions, rows whose bf16 band overflowed in the tensor-core pruner, 0...}.
  * Results are exact: candidates are pruned with a proven error band and re-ranked in float64;
  * rows whose candidate buffer overflows are recomputed by an exact float64 brute-force kernel.
  */

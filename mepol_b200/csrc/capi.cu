@@ -116,7 +116,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
     p.cand = c.take<int32_t>((size_t)n_q * p.n_split * p.cap);
     p.cand_cnt = c.take<int32_t>((size_t)n_q * p.n_split);
     p.flag = c.take<unsigned char>((size_t)n_q);
-    p.fb_max_rows = (int)(n_q < 4096 ? n_q : 4096);
+    p.fb_max_rows = (int)(n_q < 16384 ? n_q : 16384);   // rows the chunk-parallel exact fallback can take
     p.fb_list = c.take<int32_t>((size_t)p.fb_max_rows);
     p.fb_count = c.take<int>(4);
     p.fb_part_d = c.take<double>((size_t)p.fb_max_rows * fallback_chunks_for(k1) * k1);

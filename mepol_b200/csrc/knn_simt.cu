@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(kSimtThreads)
                           const float *__restrict__ rs, const float *__restrict__ r_nrm, int n_ref,
                           const float *__restrict__ glob, int d_true, int k1, int cap, int n_split,
                           int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
-                          int rescue, unsigned long long *__restrict__ stats) {
+                          int rescue, unsigned long long rescue_min_rows, unsigned long long *__restrict__ stats) {
+    // Rescue mode only pays when MANY rows overflowed the bf16 band (its CTAs sweep every reference
+    // for whatever flagged rows they own); a sparse set is cheaper in the chunk-parallel exact fallback.
+    if (rescue && stats[3] <= rescue_min_rows) return;
     constexpr int R = kSimtThreads * ROWS;
     constexpr int BN = kSimtTileRefs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -276,7 +279,8 @@ static int launch_simt_inst(const KnnPlan &p, int n_split, int cap, int rescue, 
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.n_q + R - 1) / R), (unsigned)n_split);
     kern<<<grid, kSimtThreads, smem, st>>>(p.qs, p.q_anorm, (int)p.n_q, p.rs, p.r_nrm, (int)p.n_ref, p.glob, p.d,
-                                           p.k1, cap, n_split, p.cand, p.cand_cnt, p.flag, rescue, p.stats);
+                                           p.k1, cap, n_split, p.cand, p.cand_cnt, p.flag, rescue,
+                                           (unsigned long long)p.fb_max_rows, p.stats);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (ovf) {
                         flag[row] = 1;
                         cand_cnt[row] = 0;
+                        if (stats) atomicAdd(stats + 3, 1ULL);   // rows whose bf16 band overflowed
                     } else {
                         cand_cnt[row] = cnt;
                         n_cand += cnt;

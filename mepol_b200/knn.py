@@ -31,7 +31,7 @@ class KnnResult:
 
     def stats_dict(self):
         s = self.stats.cpu().tolist()
-        return {"candidates": s[0], "fallback_rows": s[1], "compactions": s[2]}
+        return {"candidates": s[0], "fallback_rows": s[1], "compactions": s[2], "tc_overflow_rows": s[3]}
 
 
 def knn_device(ref, k1, queries=None, algo=_lib.KNN_AUTO, workspace=None, out=None):
