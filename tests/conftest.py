@@ -15,6 +15,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """Make the suite self-contained: build the C-ABI library (nvcc cross-compiles sm_100a without a
+    GPU) and the C oracle if they are missing or stale.  Both builds are incremental no-ops otherwise."""
+    import shutil
+    from mepol_b200 import build as _build
+    if shutil.which("nvcc") or os.path.exists(_build.NVCC):
+        _build.build()
+    elif not os.path.exists(_build.LIB):
+        raise RuntimeError("libmepol_b200.so is missing and nvcc is not available to build it")
+    from oracle import knn_oracle
+    knn_oracle.build()
+
+
 def golden_files(prefix):
     return sorted(glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
 
