@@ -86,6 +86,19 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.cap = 32;   // kTcSoftCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
         p.n_ref_pad = (n_ref + 127) / 128 * 128;
         p.n_q_pad = (n_q + 255) / 256 * 256;
+        {
+            // Tail balancing of the persistent grid: with few rounds (multi-GPU shards), the blocks of the
+            // last partial round are cut into reference-range splits that together fill the SMs.
+            const int64_t nrb = p.n_q_pad / 256, tiles = p.n_ref_pad / 128;
+            const int64_t rounds = nrb / sms, tail = nrb - rounds * sms;
+            p.tc_tail_split = 1;
+            if (rounds >= 1 && rounds <= 12 && tail > 0 && tiles >= 512) {
+                int64_t s_ = sms / tail;
+                if (s_ > 4) s_ = 4;
+                if (s_ >= 2) p.tc_tail_split = (int)s_;
+            }
+            p.n_split = p.tc_tail_split;
+        }
     }
     // a query slice of the fitted matrix can reuse the packed fp32 reference rows
     if (ref && q && q >= ref && q + n_q * d <= ref + n_ref * d && ((q - ref) % d) == 0) {
@@ -202,6 +215,8 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
                   workspace_bytes, p.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MEPOL_CUDA_CHECK(cudaMemsetAsync(p.flag, 0, (size_t)n_q, st));
+    if (p.algo == MEPOL_KNN_TC && p.n_split > 1)   // rows of whole units only fill slot 0 of their candidate lists
+        MEPOL_CUDA_CHECK(cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * (size_t)n_q * p.n_split, st));
     MEPOL_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * MEPOL_KNN_NSTATS, st));
     if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
     if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;

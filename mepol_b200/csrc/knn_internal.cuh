@@ -29,6 +29,7 @@ struct KnnPlan {
     int cap;           // candidate slots per (row, split)
     int n_split;       // reference-range splits (more CTAs for small batches)
     int mean_blocks;
+    int tc_tail_split; // reference-range splits of the row blocks in the last, partial round (knn_tc.cu)
     bool q_is_ref;     // query rows alias the packed reference rows
     int64_t q_row0;    // first reference row of the query slice when q_is_ref
     // workspace slices

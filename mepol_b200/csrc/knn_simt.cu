@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kSimtThreads)
                           const float *__restrict__ rs, const float *__restrict__ r_nrm, int n_ref,
                           const float *__restrict__ glob, int d_true, int k1, int cap, int n_split,
                           int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
-                          int rescue, unsigned long long rescue_min_rows, unsigned long long *__restrict__ stats) {
+                          int rescue, unsigned long long rescue_min_rows, int addr_nsplit,
+                          unsigned long long *__restrict__ stats) {
     // Rescue mode only pays when MANY rows overflowed the bf16 band (its CTAs sweep every reference
     // for whatever flagged rows they own); a sparse set is cheaper in the chunk-parallel exact fallback.
     if (rescue && stats[3] <= rescue_min_rows) return;
@@ -241,14 +242,19 @@ __global__ void __launch_bounds__(kSimtThreads)
             coop_compact(r, L);
         }
         if (active[r]) {
-            const size_t slot = (size_t)row[r] * n_split + split;
+            // addr_nsplit = candidate lists per row in the output layout (differs from n_split only in
+            // rescue mode, where this single sweep replaces all lists of the row)
+            const size_t slot = (size_t)row[r] * addr_nsplit + split;
             if (ovf[r]) {
                 flag[row[r]] = 1;
                 cand_cnt[slot] = 0;
             } else {
                 cand_cnt[slot] = cnt[r];
                 n_cand += cnt[r];
-                if (rescue) flag[row[r]] = 0;          // re-pruned successfully: back to the normal re-rank
+                if (rescue) {
+                    flag[row[r]] = 0;                  // re-pruned successfully: back to the normal re-rank
+                    for (int s2 = 1; s2 < addr_nsplit; ++s2) cand_cnt[slot + s2] = 0;
+                }
             }
         }
         __syncwarp();
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(kSimtThreads)
             const int nL = __shfl_sync(0xffffffffu, (active[r] && !ovf[r]) ? cnt[r] : 0, L);
             const int rowL = __shfl_sync(0xffffffffu, row[r], L);
             const int baseL = (r * kSimtThreads + warp0 + L) * stride;
-            for (int e = lane; e < nL; e += 32) cand[((size_t)rowL * n_split + split) * cap + e] = bufi[baseL + e];
+            for (int e = lane; e < nL; e += 32) cand[((size_t)rowL * addr_nsplit + split) * cap + e] = bufi[baseL + e];
         }
         __syncwarp();
     }
@@ -280,7 +286,7 @@ static int launch_simt_inst(const KnnPlan &p, int n_split, int cap, int rescue, 
     dim3 grid((unsigned)((p.n_q + R - 1) / R), (unsigned)n_split);
     kern<<<grid, kSimtThreads, smem, st>>>(p.qs, p.q_anorm, (int)p.n_q, p.rs, p.r_nrm, (int)p.n_ref, p.glob, p.d,
                                            p.k1, cap, n_split, p.cand, p.cand_cnt, p.flag, rescue,
-                                           (unsigned long long)p.fb_max_rows, p.stats);
+                                           (unsigned long long)p.fb_max_rows, rescue ? p.n_split : n_split, p.stats);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

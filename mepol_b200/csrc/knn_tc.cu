@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const float *__restrict__ q_delta, int n_q, const uint16_t *__restrict__ rb, int n_ref,
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
                         int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
-                        unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode) {
+                        unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode, int n_full_blocks,
+                        int tail_split, int n_split) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +96,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int tiles = kDump ? 1 : n_ref_tiles;
+    // Work units.  Row blocks [0, n_full_blocks) are whole units (all reference tiles).  The remaining
+    // "tail" blocks -- the last, partially filled round of the persistent grid, which matters when a
+    // multi-GPU shard leaves only a few rounds -- are cut into tail_split reference ranges each, so the
+    // last round keeps all SMs busy for 1/tail_split of a round.  Splits of a row write separate
+    // candidate lists (slot sp of n_split) that the re-rank merges.
+    const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * tail_split;
+    const int tiles_per_split = (n_ref_tiles + tail_split - 1) / tail_split;
+    auto unit_of = [&](int u, int &rblk, int &sp, int &tile0) {
+        if (u < n_full_blocks) {
+            rblk = u;
+            sp = 0;
+            tile0 = 0;
+            return kDump ? 1 : n_ref_tiles;
+        }
+        const int v = u - n_full_blocks;
+        rblk = n_full_blocks + v / tail_split;
+        sp = v - (v / tail_split) * tail_split;
+        tile0 = sp * tiles_per_split;
+        int hi = tile0 + tiles_per_split;
+        if (hi > n_ref_tiles) hi = n_ref_tiles;
+        return hi - tile0;
+    };
     // Register re-distribution at warpgroup granularity (setmaxnreg): the epilogue keeps a whole
     // 128-column row in registers, the producer / issuer / idle warps need almost none.
     if (warp >= kTcEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcAuxRegs));
@@ -104,17 +126,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ===================== bulk-copy producer =====================
         if (lane == 0) {
             uint32_t it = 0, rbi = 0;
-            for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x, ++rbi) {
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
+                int rblk, sp, tile0;
+                const int tiles = unit_of(u, rblk, sp, tile0);
                 mbar_wait(bar_a_empty, (rbi & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_a_full, 2 * kTcTileBytes);
                 bulk_g2s(sbase + kSmemA, qb + (size_t)rblk * kTcRows * kTcKPad, 2 * kTcTileBytes, bar_a_full);
                 // The sweep over the reference tiles starts at the row block's own position: CTAs do
                 // not hit the same L2 lines at the same moment, and in a self-search the rows' own
                 // neighbourhood (same trajectory) is seen first, which tightens tau early.
-                const int rot = kDump ? 0 : (rblk * 2) % n_ref_tiles;
+                const int rot = kDump ? 0 : (rblk * 2) % tiles;
                 for (int j = 0; j < tiles; ++j, ++it) {
                     int jt = j + rot;
-                    if (jt >= n_ref_tiles) jt -= n_ref_tiles;
+                    if (jt >= tiles) jt -= tiles;
+                    jt += tile0;
                     const uint32_t st = it % kTcStages;
                     mbar_wait(bar_done + 8 * st, ((it / kTcStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(bar_full + 8 * st, kTcTileBytes);
@@ -135,7 +160,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 a_desc[t][ks] = umma_desc(sbase + kSmemA + t * kTcTileBytes + ks * 256, 128, 512);
         const uint64_t b_desc0 = umma_desc(sbase + kSmemB, 128, 512);
         uint32_t it = 0, rbi = 0;
-        for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x, ++rbi) {
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
+            int rblk, sp, tile0;
+            const int tiles = unit_of(u, rblk, sp, tile0);
             mbar_wait(bar_a_full, rbi & 1);
             for (int j = 0; j < tiles; ++j, ++it) {
                 const uint32_t st = it % kTcStages;
@@ -251,7 +278,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
         };
 
-        for (int rblk = blockIdx.x; rblk < n_row_blocks; rblk += gridDim.x) {
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int rblk, sp, tile0;
+            const int tiles = unit_of(u, rblk, sp, tile0);
             const int row = rblk * kTcRows + rloc;
             const bool live = row < n_q;
             float tau = live ? INF : -INF;             // padding rows never collect anything
@@ -260,10 +289,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             bool ovf = false;
 #pragma unroll
             for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
-            const int rot = kDump ? 0 : (rblk * 2) % n_ref_tiles;
+            const int rot = kDump ? 0 : (rblk * 2) % tiles;
             for (int j = 0; j < tiles; ++j, ++it) {
                 int jt = j + rot;
-                if (jt >= n_ref_tiles) jt -= n_ref_tiles;
+                if (jt >= tiles) jt -= tiles;
+                jt += tile0;
                 const uint32_t buf = it & 1;
                 const uint32_t st = it % kTcStages;
                 if (!next_ready) mbar_wait(bar_done + 8 * st, (it / kTcStages) & 1);
@@ -385,10 +415,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (live) {
                     if (ovf) {
                         flag[row] = 1;
-                        cand_cnt[row] = 0;
+                        cand_cnt[(size_t)row * n_split + sp] = 0;
                         if (stats) atomicAdd(stats + 3, 1ULL);   // rows whose bf16 band overflowed
                     } else {
-                        cand_cnt[row] = cnt;
+                        cand_cnt[(size_t)row * n_split + sp] = cnt;
                         n_cand += cnt;
                     }
                 }
@@ -396,7 +426,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int L = 0; L < 32; ++L) {
                     const int nL = __shfl_sync(0xffffffffu, (live && !ovf) ? cnt : 0, L);
                     const int rowL = rblk * kTcRows + warp_row0 + L;
-                    if (lane < nL) cand[(size_t)rowL * kTcSoftCap + lane] = bufi[(warp_row0 + L) * kTcBufStride + lane];
+                    if (lane < nL)
+                        cand[((size_t)rowL * n_split + sp) * kTcSoftCap + lane] = bufi[(warp_row0 + L) * kTcBufStride + lane];
                 }
                 __syncwarp();
             }
@@ -427,7 +458,9 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     const int n_row_blocks = (int)(p.n_q_pad / kTcRows);
     const int n_ref_tiles = (int)(p.n_ref_pad / kTcTileRefs);
     int grid = device_sm_count();
-    if (grid > n_row_blocks) grid = n_row_blocks;
+    const int n_full_blocks = p.tc_tail_split > 1 ? (n_row_blocks / grid) * grid : n_row_blocks;
+    const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * p.tc_tail_split;
+    if (grid > n_units) grid = n_units;
 #ifdef MEPOL_BRINGUP
     const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up timing aid (results invalid when set):
     const int epi_mode = em ? atoi(em) : 0;              // 1 = TMEM loads only, 2 = barriers + MMA only
@@ -436,7 +469,7 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
 #endif
     kern<<<grid, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
                                                n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, nullptr,
-                                               epi_mode);
+                                               epi_mode, n_full_blocks, p.tc_tail_split, p.n_split);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
@@ -446,7 +479,7 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
     auto kern = knn_prune_tc_kernel<true, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
-                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0);
+                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
