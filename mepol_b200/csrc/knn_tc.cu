@@ -70,16 +70,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // barrier slots.  done[s]: the MMAs that read B stage s have retired (tcgen05.commit): the stage
     // may be refilled AND the accumulators they wrote are ready -- one commit serves both consumers.
     const uint32_t bar_full = sbase + kSmemBar;                    // [stages] producer -> issuer
-    const uint32_t bar_done = bar_full + 8 * kTcStages;            // [stages] issuer -> producer + epilogue
-    const uint32_t bar_acc_empty = bar_done + 8 * kTcStages;       // [2]      epilogue -> issuer
+    const uint32_t bar_done = bar_full + 8 * kTcStages;            // [stages] issuer -> producer + epilogue of accumulator 1
+    const uint32_t bar_done0 = bar_done + 8 * kTcStages;           // [stages] issuer -> epilogue of accumulator 0 (early commit)
+    const uint32_t bar_acc_empty = bar_done0 + 8 * kTcStages;      // [2]      epilogue -> issuer
     const uint32_t bar_a_full = bar_acc_empty + 16;
     const uint32_t bar_a_empty = bar_a_full + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (2 * kTcStages + 4));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (3 * kTcStages + 4));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_done + 8 * s, 1);
+            mbar_init(bar_done0 + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps);
         mbar_init(bar_a_full, 1);
@@ -178,13 +180,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     // one K=16 step = two 16-byte k-chunks = 256 bytes further along K
                     const uint64_t bd0 = b_desc0 + (uint64_t)((st * kTcTileBytes) >> 4);
                     const uint64_t bd1 = bd0 + (256 >> 4);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const uint32_t d_addr = tmem_base + buf * 256 + t * 128;
-                        tc_mma_bf16(d_addr, a_desc[t][0], bd0, kTcIdesc, 0);
-                        tc_mma_bf16(d_addr, a_desc[t][1], bd1, kTcIdesc, 1);
-                    }
-                    tc_commit(bar_done + 8 * st);
+                    // accumulator 0 is committed on its own: its four epilogue warps start ~190 cycles
+                    // before those of accumulator 1, so the two warps that share an SM sub-partition
+                    // do not run their min trees on the ALU pipe at the same time
+                    const uint32_t d0 = tmem_base + buf * 256;
+                    tc_mma_bf16(d0, a_desc[0][0], bd0, kTcIdesc, 0);
+                    tc_mma_bf16(d0, a_desc[0][1], bd1, kTcIdesc, 1);
+                    tc_commit(bar_done0 + 8 * st);
+                    tc_mma_bf16(d0 + 128, a_desc[1][0], bd0, kTcIdesc, 0);
+                    tc_mma_bf16(d0 + 128, a_desc[1][1], bd1, kTcIdesc, 1);
+                    tc_commit(bar_done + 8 * st);   // commits retire in order: this one also covers the stage
                 }
                 __syncwarp();
             }
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int my_base = rloc * kTcBufStride;
         const float A = glob[G_AMAX], D = glob[G_DELTA_MAX];
         const float INF = __int_as_float(0x7f800000);
+        const uint32_t my_done = t == 0 ? bar_done0 : bar_done;
         uint32_t it = 0;
         unsigned n_compactions = 0;
         unsigned long long n_cand = 0;
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 jt += tile0;
                 const uint32_t buf = it & 1;
                 const uint32_t st = it % kTcStages;
-                if (!next_ready) mbar_wait(bar_done + 8 * st, (it / kTcStages) & 1);
+                if (!next_ready) mbar_wait(my_done + 8 * st, (it / kTcStages) & 1);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + lane_base + buf * 256 + t * 128;
                 // pull the thread's whole 128-column row into registers and hand the TMEM buffer
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (epi_mode != 2) tc_ld128(tbase, v);
                 {   // probe the next tile's barrier while the TMEM loads are in flight
                     const uint32_t st1 = (it + 1) % kTcStages;
-                    next_ready = mbar_test_wait(bar_done + 8 * st1, ((it + 1) / kTcStages) & 1);
+                    next_ready = mbar_test_wait(my_done + 8 * st1, ((it + 1) / kTcStages) & 1);
                 }
                 if (epi_mode != 2) tc_wait_ld();
                 tc_fence_before();
