@@ -28,6 +28,7 @@ namespace mepol {
 
 constexpr int kScanThreads = 256;
 constexpr int kGatherThreads = 256;
+constexpr int kGatherRows = 4;      // rows per thread of the gather kernel (memory-level parallelism)
 constexpr double kLogPi = 1.1447298858494001741434273513531;
 
 struct IwWorkspace {
@@ -38,7 +39,10 @@ struct IwWorkspace {
     size_t bytes;
 };
 
-static int gather_blocks_for(int64_t n) { return (int)((n + kGatherThreads - 1) / kGatherThreads); }
+static int gather_blocks_for(int64_t n) {
+    const int64_t per = (int64_t)kGatherThreads * kGatherRows;
+    return (int)((n + per - 1) / per);
+}
 
 static void carve_iw(IwWorkspace &w, int64_t n, int64_t n_traj, void *ws) {
     Carver c(ws);
@@ -198,41 +202,55 @@ __global__ void __launch_bounds__(kGatherThreads)
     __shared__ double s_warp[32];
     __shared__ unsigned s_ticket;
     const int k = k1 - 1;
-    const int i = blockIdx.x * kGatherThreads + threadIdx.x;
     const double M = scal[3], S = scal[4];
+    // per-thread constants, amortised over kGatherRows rows
+    const double inv_S = 1.0 / S, inv_k = 1.0 / (double)k;
+    const double log_k_over_n = log((double)k) - log((double)n);
+    const double logV_const = 0.5 * (double)ns * kLogPi - log_G;
+    const T Mt = (T)M;
     double h_term = 0.0, kl_term = 0.0, s_term = 0.0, bad = 0.0;
-    if (i < n) {
-        const int32_t *ir = idx + (size_t)i * k1;
-        // W_i in the storage precision's exp, accumulated in double
-        double W = 0.0;
-        const T Mt = (T)M;
-        for (int m = 0; m < k; ++m) W += (double)RowMath<T>::exp_(c[ir[m]] - Mt);
-        W /= S;
-        const double inv_k = 1.0 / (double)k;
-        double g;
+    // gather phase first for every row of the thread: kGatherRows * k independent loads in flight
+    double Wr[kGatherRows];
+#pragma unroll
+    for (int r = 0; r < kGatherRows; ++r) {
+        const int i = (blockIdx.x * kGatherRows + r) * kGatherThreads + threadIdx.x;
+        Wr[r] = 0.0;
+        if (i < n) {
+            const int32_t *ir = idx + (size_t)i * k1;
+            double W = 0.0;
+            for (int m = 0; m < k; ++m) W += (double)RowMath<T>::exp_(c[ir[m]] - Mt);   // storage-precision exp, fp64 sum
+            Wr[r] = W * inv_S;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kGatherRows; ++r) {
+        const int i = (blockIdx.x * kGatherRows + r) * kGatherThreads + threadIdx.x;
+        if (i >= n) continue;
+        const double W = Wr[r];
+        double g, ht, kt;
         if (eps == 0.0) {
             // log-space: log q = log W - log V, log V = ns log r + (ns/2) log pi - lgamma(ns/2+1);
             // r^ns overflows float32 already for ns=29, r>~20 -- never formed explicitly.
             const T logW = RowMath<T>::log_((T)W);
             const T logr = RowMath<T>::log_(rk[i]);
-            const double logV = (double)ns * (double)logr + 0.5 * (double)ns * kLogPi - log_G;
-            const double logq = (double)logW - logV;
-            h_term = (W * inv_k) * logq;
+            const double logq = (double)logW - ((double)ns * (double)logr + logV_const);
+            ht = (W * inv_k) * logq;
             g = -inv_k * (logq + 1.0);
-            kl_term = log((double)k) - log((double)n) - (double)logW;
+            kt = log_k_over_n - (double)logW;
         } else {
             // literal float64 evaluation of mepol.py:150-152,165 (MountainCar's eps=1e-15)
-            const double r = (double)rk[i];
-            const double V = pow(r, (double)ns) * exp(0.5 * (double)ns * kLogPi) / exp(log_G);
+            const double rr = (double)rk[i];
+            const double V = pow(rr, (double)ns) * exp(0.5 * (double)ns * kLogPi) / exp(log_G);
             const double qv = W / (V + eps);
-            h_term = (W * inv_k) * log(qv + eps);
+            ht = (W * inv_k) * log(qv + eps);
             g = -inv_k * (log(qv + eps) + qv / (qv + eps));
-            kl_term = log((double)k / ((double)n * W) + eps);
+            kt = log((double)k / ((double)n * W) + eps);
         }
         if (gW) gW[i] = (T)g;
-        s_term = g * W;
-        if (!(h_term == h_term) || !(kl_term == kl_term) || fabs(h_term) == INFINITY || fabs(kl_term) == INFINITY)
-            bad = 1.0;
+        h_term += ht;
+        kl_term += kt;
+        s_term += g * W;
+        if (!(ht == ht) || !(kt == kt) || fabs(ht) == INFINITY || fabs(kt) == INFINITY) bad += 1.0;
     }
     const double bh = block_reduce_sum(h_term, s_warp);
     const double bk = block_reduce_sum(kl_term, s_warp);
@@ -396,18 +414,33 @@ __global__ void __launch_bounds__(kWarpScanWarps * 32)
     }
 }
 
+// Backward in the many-trajectories regime, two launches:
+//   iw_bwd_elem    one thread per particle (full occupancy for the latency-bound CSR gathers):
+//                  g_c[j] = w_j (sum_{e in rev[j]} gW[col[e]] - s), written into the output buffer
+//   iw_bwd_rscan   one warp per trajectory: reverse inclusive scan of g_c in place, times grad_H
+template <typename T>
+__global__ void __launch_bounds__(256)
+    iw_bwd_elem_kernel(const T *__restrict__ c, const T *__restrict__ gW, const double *__restrict__ scal, int n,
+                       const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, T *__restrict__ gc_out) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const double M = scal[3], S = scal[4], s = scal[2];
+    double gw = 0.0;
+    const int e0 = rowptr[j], e1 = rowptr[j + 1];
+    for (int e = e0; e < e1; ++e) gw += (double)gW[col[e]];
+    const double w = (double)RowMath<T>::exp_(c[j] - (T)M) / S;
+    gc_out[j] = (T)(w * (gw - s));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarpScanWarps * 32)
-    iw_bwd_warp_kernel(const T *__restrict__ c, const T *__restrict__ gW, const double *__restrict__ scal,
-                       const int32_t *__restrict__ traj_off, int n_traj, const int32_t *__restrict__ rowptr,
-                       const int32_t *__restrict__ col, const double *__restrict__ grad_H, T *__restrict__ grad_lt) {
+    iw_bwd_rscan_kernel(const int32_t *__restrict__ traj_off, int n_traj, const double *__restrict__ grad_H,
+                        T *__restrict__ g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * kWarpScanWarps + warp;
     if (t >= n_traj) return;
     const int lo = traj_off[t], hi = traj_off[t + 1];
-    const double M = scal[3], S = scal[4], s = scal[2];
     const double gH = grad_H[0];
-    const T Mt = (T)M;
     double carry = 0.0;
     // walk backwards: position p = 0 is the LAST step of the trajectory
     for (int base = 0; base < hi - lo; base += 128) {
@@ -415,21 +448,14 @@ __global__ void __launch_bounds__(kWarpScanWarps * 32)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = hi - 1 - (base + 32 * u + lane);
-            gc[u] = 0.0;
-            if (j >= lo) {
-                double gw = 0.0;
-                const int e0 = rowptr[j], e1 = rowptr[j + 1];
-                for (int e = e0; e < e1; ++e) gw += (double)gW[col[e]];
-                const double w = (double)RowMath<T>::exp_(c[j] - Mt) / S;
-                gc[u] = w * (gw - s);
-            }
+            gc[u] = j >= lo ? (double)g[j] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = hi - 1 - (base + 32 * u + lane);
             const double incl = warp_inclusive_scan(gc[u], lane) + carry;
             carry = __shfl_sync(0xffffffffu, incl, 31);
-            if (j >= lo) grad_lt[j] = (T)(gH * incl);
+            if (j >= lo) g[j] = (T)(gH * incl);
         }
     }
 }
@@ -626,8 +652,11 @@ static int iw_bwd_impl(const T *c, const T *gW, const double *scal, const int32_
     MEPOL_REQUIRE(n > 0 && n_traj > 0, MEPOL_E_INVALID, "iw_entropy_bwd: bad sizes");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_traj >= kWarpPathMinTraj)
-        iw_bwd_warp_kernel<T><<<(int)((n_traj + kWarpScanWarps - 1) / kWarpScanWarps), kWarpScanWarps * 32, 0, st>>>(
-            c, gW, scal, traj_off, (int)n_traj, rowptr, col, grad_H, grad_lt);
+    {
+        iw_bwd_elem_kernel<T><<<(int)((n + 255) / 256), 256, 0, st>>>(c, gW, scal, (int)n, rowptr, col, grad_lt);
+        iw_bwd_rscan_kernel<T><<<(int)((n_traj + kWarpScanWarps - 1) / kWarpScanWarps), kWarpScanWarps * 32, 0, st>>>(
+            traj_off, (int)n_traj, grad_H, grad_lt);
+    }
     else
         iw_bwd_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(c, gW, scal, traj_off, rowptr, col, grad_H, grad_lt);
     MEPOL_CUDA_CHECK(cudaGetLastError());
