@@ -50,7 +50,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
     MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC, MEPOL_E_INVALID,
                   "knn: unknown algo %d", algo);
     // AUTO: tensor cores pay off for wide particles and large batches; for d < 16 (the regime where
-    // sklearn itself switches to a kd-tree, neighbors/_base.py:615-626) the bf16 band is too coarse
+    // sklearn itself switches to a kd-tree, neighbors/_base.py:615-626) the fp16 band is too coarse
     // for the tiny neighbour radii and the fp32 SIMT pruner is both exact-band-tight and cheap.
     if (algo == MEPOL_KNN_AUTO)
         algo = (tc_supported(d, k1) && n_ref >= 4096 && d >= 16) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
@@ -106,8 +106,8 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.q_row0 = (q - ref) / d;
     }
     Carver c(ws);
-    p.mean_partial = c.take<double>((size_t)p.mean_blocks * MEPOL_MAX_DIM);
-    p.mean = c.take<double>(MEPOL_MAX_DIM);
+    p.mean_partial = c.take<double>((size_t)p.mean_blocks * 3 * MEPOL_MAX_DIM);   // sum, min, max
+    p.mean = c.take<double>(MEPOL_MAX_DIM + 2);   // column means + the operand scale
     p.glob = c.take<float>(G_COUNT);
     p.stats = c.take<unsigned long long>(MEPOL_KNN_NSTATS);
     p.r_anorm = c.take<float>((size_t)n_ref);
@@ -228,7 +228,7 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
     if (rc != MEPOL_OK) return rc;
-    // rows whose bf16 band overflowed are re-pruned with the fp32 band before the exact fallback
+    // rows whose fp16 band overflowed are re-pruned with the fp32 band before the exact fallback
     if (p.algo == MEPOL_KNN_TC && (rc = launch_rescue_simt(p, st)) != MEPOL_OK) return rc;
 #ifdef MEPOL_BRINGUP
     {

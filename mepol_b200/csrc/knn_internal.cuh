@@ -6,9 +6,11 @@ namespace mepol {
 
 constexpr int kSimtThreads = 128;  // one query row (or two) per thread
 constexpr int kSimtTileRefs = 64;  // reference rows staged per shared-memory tile
-constexpr int kTcKPad = 32;        // bf16 operand width of the tensor-core pruner (d + 3 norm columns <= 32)
+constexpr double kTcScaledNormMax = 128.0;   // centred rows are scaled to norms <= this (fp16 range)
+constexpr double kTcQueryAbsMax = 30000.0;   // scaled query entries beyond this do not fit fp16
+constexpr int kTcKPad = 32;        // fp16 operand width of the tensor-core pruner (d + 3 norm columns <= 32)
 
-// Element index (in bf16 units) of (row, column c) inside the tensor-core operand arrays: 128-row
+// Element index (in fp16 units) of (row, column c) inside the tensor-core operand arrays: 128-row
 // tiles of 8 KB, each tile in UMMA canonical K-major no-swizzle order (8-row x 16-byte core
 // matrices of 128 B; next core matrix along K at +128 B, next 8-row group at +512 B).
 __host__ __device__ inline size_t tc_elem_index(int64_t row, int c) {
@@ -39,7 +41,7 @@ struct KnnPlan {
     int32_t *cand, *cand_cnt;
     unsigned char *flag;
     unsigned long long *stats;
-    // tensor-core pruner operands (bf16 stored as uint16), padded to tile multiples
+    // tensor-core pruner operands (fp16 stored as uint16), padded to tile multiples
     uint16_t *rb, *qb;
     float *q_delta;
     int64_t n_ref_pad, n_q_pad;

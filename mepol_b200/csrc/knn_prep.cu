@@ -4,13 +4,13 @@
 //  _middle_term_computer.pyx.tp:329-396 float32->float64 upcast copies).
 //
 // All per-row arithmetic is float64 (B200 has full-rate-enough fp64 and the pass is a single
-// streaming read of X): x' = x - mean exactly, ||x'||^2 exactly, then
+// streaming read of X): x' = sigma * (x - mean) exactly (sigma = 2^e keeps fp16 in range), ||x'||^2 exactly, then
 //   SIMT operand   xs[row][0..dpad)  = fl32(x')               (zero padded)
 //   r_nrm[row]     = fl32(||x'||^2), r_anorm[row] >= ||x'||   (rounded up)
-//   TC operand     xb[row][0..32)    = bf16 row (see knn_tc.cu for the column meaning)
-//   q_delta[row]   >= ||bf16(x') - x'||  (rounded up), and global maxima via atomicMax on the
+//   TC operand     xb[row][0..32)    = fp16 row (see knn_tc.cu for the column meaning)
+//   q_delta[row]   >= ||fp16(x') - x'||  (rounded up), and global maxima via atomicMax on the
 //   (non-negative) float bit patterns.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "knn_internal.cuh"
 
@@ -23,32 +23,75 @@ constexpr int kMeanRowsPerBlock = 1024;
 __global__ void __launch_bounds__(kMeanThreadsX *kMeanThreadsY)
     col_sum_partial_kernel(const float *__restrict__ x, int64_t n, int d, double *__restrict__ partial) {
     __shared__ double sm[kMeanThreadsY][kMeanThreadsX];
+    __shared__ float smin[kMeanThreadsY][kMeanThreadsX], smax[kMeanThreadsY][kMeanThreadsX];
     const int cx = threadIdx.x, ry = threadIdx.y;
     const int64_t row0 = (int64_t)blockIdx.x * kMeanRowsPerBlock;
     int64_t row1 = row0 + kMeanRowsPerBlock;
     if (row1 > n) row1 = n;
     double s = 0.0;
+    float lo = __int_as_float(0x7f800000), hi = -lo;
     if (cx < d)
-        for (int64_t r = row0 + ry; r < row1; r += kMeanThreadsY) s += (double)x[r * d + cx];
+        for (int64_t r = row0 + ry; r < row1; r += kMeanThreadsY) {
+            const float v = x[r * d + cx];
+            s += (double)v;
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        }
     sm[ry][cx] = s;
+    smin[ry][cx] = lo;
+    smax[ry][cx] = hi;
     __syncthreads();
     if (ry == 0 && cx < d) {
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < kMeanThreadsY; ++i) t += sm[i][cx];
-        partial[(int64_t)blockIdx.x * MEPOL_MAX_DIM + cx] = t;
+        for (int i = 0; i < kMeanThreadsY; ++i) {
+            t += sm[i][cx];
+            lo = fminf(lo, smin[i][cx]);
+            hi = fmaxf(hi, smax[i][cx]);
+        }
+        double *o = partial + (int64_t)blockIdx.x * (3 * MEPOL_MAX_DIM);
+        o[cx] = t;
+        o[MEPOL_MAX_DIM + cx] = (double)lo;
+        o[2 * MEPOL_MAX_DIM + cx] = (double)hi;
     }
 }
 
 __global__ void col_mean_final_kernel(const double *__restrict__ partial, int n_blocks, int64_t n, int d,
                                       double *__restrict__ mean, float *__restrict__ glob) {
+    __shared__ double r2[64];
     const int c = threadIdx.x;
+    double ext = 0.0;
     if (c < d) {
-        double t = 0.0;
-        for (int b = 0; b < n_blocks; ++b) t += partial[(int64_t)b * MEPOL_MAX_DIM + c];  // fixed order
+        double t = 0.0, lo = 1e300, hi = -1e300;
+        for (int b = 0; b < n_blocks; ++b) {           // fixed order
+            const double *pb = partial + (int64_t)b * (3 * MEPOL_MAX_DIM);
+            t += pb[c];
+            lo = fmin(lo, pb[MEPOL_MAX_DIM + c]);
+            hi = fmax(hi, pb[2 * MEPOL_MAX_DIM + c]);
+        }
         // The mean only has to be the SAME value for queries and references; rounding it to
         // float keeps x - mean exactly representable in float64 for every float32 input.
-        mean[c] = (double)(float)(t / (double)n);
+        const double m = (double)(float)(t / (double)n);
+        mean[c] = m;
+        ext = fmax(hi - m, m - lo);
+    }
+    r2[c] = ext * ext;
+    __syncthreads();
+    if (c == 0) {
+        // Power-of-two scale sigma with sigma * max_row ||x - mean|| <= kTcScaledNormMax, from the
+        // per-column extents (an upper bound of the max norm).  Scaling by 2^e is exact, so the
+        // fp32 operands lose nothing; the fp16 tensor-core operands stay inside fp16's range
+        // (entries -2*y~ <= 2*128, ||y'||^2 <= 16384).
+        double a2 = 0.0;
+        for (int i = 0; i < d; ++i) a2 += r2[i];
+        int e = 0;
+        const double ab = sqrt(a2);
+        if (ab > 0.0 && ab < 1e300) {
+            e = (int)floor(log2(kTcScaledNormMax / ab));
+            while (ldexp(ab, e) > kTcScaledNormMax) --e;
+            e = max(-100, min(100, e));
+        }
+        mean[MEPOL_MAX_DIM] = ldexp(1.0, e);
     }
     if (c < G_COUNT) glob[c] = 0.0f;
 }
@@ -63,7 +106,7 @@ int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cu
 
 int mean_blocks_for(int64_t n_ref) { return (int)((n_ref + kMeanRowsPerBlock - 1) / kMeanRowsPerBlock); }
 
-// One thread per row.  dpad is the SIMT operand width; when xb != nullptr the bf16 tensor-core
+// One thread per row.  dpad is the SIMT operand width; when xb != nullptr the fp16 tensor-core
 // operand is produced as well (refs: [-2*y~ (d cols), n_hi, n_mid, n_lo, 0...]; queries:
 // [x~ (d cols), 1, 1, 1, 0...]) -- see knn_tc.cu.
 __global__ void __launch_bounds__(128)
@@ -74,24 +117,19 @@ __global__ void __launch_bounds__(128)
     __shared__ double smean[MEPOL_MAX_DIM];
     if (threadIdx.x < d) smean[threadIdx.x] = mean[threadIdx.x];
     __syncthreads();
+    const double sigma = mean[MEPOL_MAX_DIM];
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float a_up = 0.f, delta_up = 0.f, atilde_up = 0.f;
     if (row < n) {
         const float *xr = x + row * d;
         float *o = xs ? xs + row * dpad : nullptr;
         double n2 = 0.0, dl2 = 0.0, nt2 = 0.0;
+        bool in_range = true;
         for (int c = 0; c < d; ++c) {
-            double v = (double)xr[c] - smean[c];
+            const double v = ((double)xr[c] - smean[c]) * sigma;   // exact: sigma is a power of two
             n2 += v * v;
             if (o) o[c] = (float)v;
-            if (xb) {
-                __nv_bfloat16 hb = __double2bfloat16(v);
-                double hv = (double)__bfloat162float(hb);
-                dl2 += (hv - v) * (hv - v);
-                nt2 += hv * hv;
-                __nv_bfloat16 st = is_ref ? __float2bfloat16(-2.0f * __bfloat162float(hb)) : hb;  // x2 exact
-                xb[tc_elem_index(row, c)] = __bfloat16_as_ushort(st);
-            }
+            in_range = in_range && fabs(v) <= kTcQueryAbsMax;
         }
         if (o)
             for (int c = d; c < dpad; ++c) o[c] = 0.f;
@@ -99,21 +137,32 @@ __global__ void __launch_bounds__(128)
         a_up = __double2float_ru(sqrt(n2) * (1.0 + 1e-12));
         anorm[row] = a_up;
         if (xb) {
-            delta_up = __double2float_ru(sqrt(dl2) * (1.0 + 1e-12));
+            // fp16 operand.  A query far outside the fitted set's extent (fp16 would overflow) gets a
+            // zero operand and an infinite band: the kernel flags it and the exact fallback serves it.
+            for (int c = 0; c < d; ++c) {
+                const double v = in_range ? ((double)xr[c] - smean[c]) * sigma : 0.0;
+                const __half hb = __double2half(v);
+                const double hv = (double)__half2float(hb);
+                dl2 += (hv - v) * (hv - v);
+                nt2 += hv * hv;
+                const __half st = is_ref ? __float2half(-2.0f * __half2float(hb)) : hb;   // x2 exact
+                xb[tc_elem_index(row, c)] = __half_as_ushort(st);
+            }
+            delta_up = in_range ? __double2float_ru(sqrt(dl2) * (1.0 + 1e-12)) : __int_as_float(0x7f800000);
             atilde_up = __double2float_ru(sqrt(nt2) * (1.0 + 1e-12));
             if (delta) delta[row] = delta_up;
             if (is_ref) {
-                // ||y'||^2 split over three bf16 columns: hi + mid + lo reproduces it to ~2^-24
-                __nv_bfloat16 h = __double2bfloat16(n2);
-                double r1 = n2 - (double)__bfloat162float(h);
-                __nv_bfloat16 m = __double2bfloat16(r1);
-                double r2 = r1 - (double)__bfloat162float(m);
-                __nv_bfloat16 l = __double2bfloat16(r2);
-                xb[tc_elem_index(row, d)] = __bfloat16_as_ushort(h);
-                xb[tc_elem_index(row, d + 1)] = __bfloat16_as_ushort(m);
-                xb[tc_elem_index(row, d + 2)] = __bfloat16_as_ushort(l);
+                // ||y'||^2 split over three fp16 columns: hi + mid + lo reproduces it to ~2^-24
+                const __half h = __double2half(n2);
+                const double r1 = n2 - (double)__half2float(h);
+                const __half m = __double2half(r1);
+                const double r2 = r1 - (double)__half2float(m);
+                const __half l = __double2half(r2);
+                xb[tc_elem_index(row, d)] = __half_as_ushort(h);
+                xb[tc_elem_index(row, d + 1)] = __half_as_ushort(m);
+                xb[tc_elem_index(row, d + 2)] = __half_as_ushort(l);
             } else {
-                const uint16_t one = __bfloat16_as_ushort(__float2bfloat16(1.0f));
+                const uint16_t one = __half_as_ushort(__float2half(1.0f));
                 xb[tc_elem_index(row, d)] = one;
                 xb[tc_elem_index(row, d + 1)] = one;
                 xb[tc_elem_index(row, d + 2)] = one;
@@ -121,9 +170,10 @@ __global__ void __launch_bounds__(128)
             for (int c = d + 3; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
         }
     } else if (row < n_pad && xb) {
-        // padding rows of the tensor-core operand: references get a huge norm so they never win
+        // padding rows of the tensor-core operand: references get a norm above every real score
+        // (real scores stay below 3 * kTcScaledNormMax^2 = 49152) so they never win
         for (int c = 0; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
-        if (is_ref) xb[tc_elem_index(row, d)] = __bfloat16_as_ushort(__float2bfloat16(3.0e38f));
+        if (is_ref) xb[tc_elem_index(row, d)] = __half_as_ushort(__float2half(60000.0f));
     }
     if (is_ref) {
         // max over the fitted set (bit patterns of non-negative floats order like unsigned ints)

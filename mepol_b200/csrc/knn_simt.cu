@@ -4,9 +4,9 @@
 // (sklearn/metrics/_pairwise_distances_reduction/_argkmin.pyx.tp:471-510: GEMM middle term + norms
 //  + heap_push for every (query, reference) pair).  Three uses:
 //   * the search itself for small particle dimensions (GridWorld / MountainCar / Ant-7d: a 2..7-wide
-//     contraction cannot feed tensor cores and bf16 is far too coarse for their tiny neighbour
+//     contraction cannot feed tensor cores and fp16 is far too coarse for their tiny neighbour
 //     radii), for k+1 > 12 (GridWorld k=50) and for d > 29 (Humanoid-47);
-//   * the RESCUE pass behind the tensor-core pruner: rows whose bf16 error band overflowed the
+//   * the RESCUE pass behind the tensor-core pruner: rows whose fp16 error band overflowed the
 //     candidate buffer (clustered / trajectory-like data, where neighbour distances are small
 //     compared with ||x||) are re-pruned here with the ~1000x tighter fp32 band before anything
 //     falls back to the exact float64 brute force.
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kSimtThreads)
                           int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
                           int rescue, unsigned long long rescue_min_rows, int addr_nsplit,
                           unsigned long long *__restrict__ stats) {
-    // Rescue mode only pays when MANY rows overflowed the bf16 band (its CTAs sweep every reference
+    // Rescue mode only pays when MANY rows overflowed the fp16 band (its CTAs sweep every reference
     // for whatever flagged rows they own); a sparse set is cheaper in the chunk-parallel exact fallback.
     if (rescue && stats[3] <= rescue_min_rows) return;
     constexpr int R = kSimtThreads * ROWS;

@@ -1,18 +1,18 @@
-// K1 (tensor-core form): tcgen05 bf16 pruning pass of the exact k-NN search for sm_100a.
+// K1 (tensor-core form): tcgen05 fp16 pruning pass of the exact k-NN search for sm_100a.
 //
 // Replaces the same reference hot loop as knn_simt.cu (sklearn ArgKmin,
 // _argkmin.pyx.tp:471-510: dgemm middle term + norms + heap_push per pair), but the
 // ||y||^2 - 2 x.y score tile is produced by the 5th-generation tensor cores:
 //
-//   A (queries)    [x~_0 .. x~_{d-1}, 1, 1, 1, 0..]            bf16, K = 32
-//   B (references) [-2y~_0 .. -2y~_{d-1}, n_hi, n_mid, n_lo, 0..] bf16, K = 32
+//   A (queries)    [x~_0 .. x~_{d-1}, 1, 1, 1, 0..]            fp16, K = 32
+//   B (references) [-2y~_0 .. -2y~_{d-1}, n_hi, n_mid, n_lo, 0..] fp16, K = 32
 //   D = A . B^T  = ||y'||^2 - 2 x~.y~   (fp32 accumulator in TMEM; the row-constant ||x'||^2 is
 //                                         dropped, it does not change a row's ranking)
 //
 // so the accumulator IS the ranking key and the epilogue does no arithmetic on it: tcgen05.ld of
 // the thread's own 128-column row, a 3-input-min tree (FMNMX3), one compare with the row's pruning
 // threshold, and a rare slow path that appends survivors to the row's candidate buffer.
-// Exactness comes from the proven error band (tc_band) and the fp64 re-rank, never from bf16.
+// Exactness comes from the proven error band (tc_band) and the fp64 re-rank, never from fp16.
 //
 // CTA = 256 query rows (two M=128 accumulators) x a stream of 128-reference B tiles.
 //   warp 8      bulk-copy producer (cp.async.bulk -> smem, mbarrier complete_tx), 4-stage ring
@@ -44,6 +44,7 @@ constexpr int kTcBufStride = kTcCap + 1;         // row-major, padded: conflict-
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcThreads = (kTcEpiWarps + 4) * 32;   // 8 epilogue warps + producer + issuer + 2 idle (whole warpgroup for setmaxnreg)
 constexpr int kTcEpiRegs = 216;                        // setmaxnreg budget of the epilogue warpgroups
+constexpr int kTcWarmTiles = 256;                      // tau-only tiles at the start of a unit (see warm_of)
 constexpr int kTcAuxRegs = 40;                         //   ... and of the producer/issuer warpgroup
 
 constexpr int kSmemA = 0;
@@ -56,6 +57,15 @@ constexpr int kSmemTotal = kSmemBar + 512;
 
 bool tc_supported(int d, int k1) { return d + 3 <= kTcKPad && 2 * k1 + 8 <= kTcSoftCap; }
 
+#ifdef MEPOL_BRINGUP
+#define TC_PROF_NOW() clock64()
+#else
+#define TC_PROF_NOW() 0LL
+#endif
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ float ld_volatile_f32(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
+
 template <bool kDump, int K1>
 __global__ void __launch_bounds__(kTcThreads, 1)
     knn_prune_tc_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
@@ -63,19 +73,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
                         int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
                         unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode, int n_full_blocks,
-                        int tail_split, int n_split) {
+                        int tail_split, int n_split, int warm_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barrier slots.  done[s]: the MMAs that read B stage s have retired (tcgen05.commit): the stage
-    // may be refilled AND the accumulators they wrote are ready -- one commit serves both consumers.
-    const uint32_t bar_full = sbase + kSmemBar;                    // [stages] producer -> issuer
-    const uint32_t bar_done = bar_full + 8 * kTcStages;            // [stages] issuer -> producer + epilogue of accumulator 1
-    const uint32_t bar_done0 = bar_done + 8 * kTcStages;           // [stages] issuer -> epilogue of accumulator 0 (early commit)
-    const uint32_t bar_acc_empty = bar_done0 + 8 * kTcStages;      // [2]      epilogue -> issuer
-    const uint32_t bar_a_full = bar_acc_empty + 16;
+    // barrier slots.  done0/done1[s]: the MMAs of accumulator 0 / 1 that read B stage s have retired
+    // (tcgen05.commit): their accumulator is ready, and once both fired the stage may be refilled.
+    const uint32_t bar_full = sbase + kSmemBar;                    // [stages] producer -> issuers
+    const uint32_t bar_done = bar_full + 8 * kTcStages;            // [stages] issuer 1 -> producer + epilogue of accumulator 1
+    const uint32_t bar_done0 = bar_done + 8 * kTcStages;           // [stages] issuer 0 -> producer + epilogue of accumulator 0
+    const uint32_t bar_acc_empty = bar_done0 + 8 * kTcStages;      // [2 buffers][2 accumulators] epilogue -> issuer
+    const uint32_t bar_a_full = bar_acc_empty + 32;
     const uint32_t bar_a_empty = bar_a_full + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (3 * kTcStages + 4));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBar + 8 * (3 * kTcStages + 6));
+    volatile uint32_t *ts_s = reinterpret_cast<volatile uint32_t *>(smem + kSmemBar + 320);   // bring-up time stamps [16]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) {
@@ -83,9 +94,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(bar_done + 8 * s, 1);
             mbar_init(bar_done0 + 8 * s, 1);
         }
-        for (int b = 0; b < 2; ++b) mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps);
+        for (int b = 0; b < 4; ++b) mbar_init(bar_acc_empty + 8 * b, kTcEpiWarps / 2);
         mbar_init(bar_a_full, 1);
-        mbar_init(bar_a_empty, 1);
+        mbar_init(bar_a_empty, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kTcEpiWarps + 1) {
@@ -120,12 +131,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (hi > n_ref_tiles) hi = n_ref_tiles;
         return hi - tile0;
     };
+    // Warm-up tiles.  A streaming top-k1 appends ~k1*ln(n) survivors per row, most of them while tau
+    // is still loose.  The first `warm` tiles of a unit are therefore only used to bound the k1-th
+    // smallest score: the k1 smallest TILE MINIMA (k1 distinct references) are tracked branch-free in
+    // registers and nothing is appended; the same tiles are swept again at the end of the unit, now
+    // against a tight tau.  ~3 % more MMA work removes ~70 % of the divergent survivor handling.
+    auto warm_of = [&](int tiles) { return (K1 > 0 && !kDump) ? min(warm_tiles, tiles >> 3) : 0; };
     // Register re-distribution at warpgroup granularity (setmaxnreg): the epilogue keeps a whole
     // 128-column row in registers, the producer / issuer / idle warps need almost none.
-    if (warp >= kTcEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcAuxRegs));
+    // (each role branch issues its own setmaxnreg so that ptxas budgets the branch it sits in)
+#define TC_AUX_SETMAXNREG() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcAuxRegs))
 
     if (warp == kTcEpiWarps) {
         // ===================== bulk-copy producer =====================
+        TC_AUX_SETMAXNREG();
         if (lane == 0) {
             uint32_t it = 0, rbi = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
@@ -138,64 +157,86 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 // not hit the same L2 lines at the same moment, and in a self-search the rows' own
                 // neighbourhood (same trajectory) is seen first, which tightens tau early.
                 const int rot = kDump ? 0 : (rblk * 2) % tiles;
-                for (int j = 0; j < tiles; ++j, ++it) {
+                const int sweep = tiles + warm_of(tiles);
+                for (int j = 0; j < sweep; ++j, ++it) {
                     int jt = j + rot;
+                    if (jt >= tiles) jt -= tiles;
                     if (jt >= tiles) jt -= tiles;
                     jt += tile0;
                     const uint32_t st = it % kTcStages;
-                    mbar_wait(bar_done + 8 * st, ((it / kTcStages) & 1) ^ 1);
+                    mbar_wait(bar_done0 + 8 * st, ((it / kTcStages) & 1) ^ 1);   // both accumulators' MMAs
+                    mbar_wait(bar_done + 8 * st, ((it / kTcStages) & 1) ^ 1);    // have read the stage
                     mbar_arrive_expect_tx(bar_full + 8 * st, kTcTileBytes);
                     bulk_g2s(sbase + kSmemB + st * kTcTileBytes, rb + (size_t)jt * kTcTileRefs * kTcKPad, kTcTileBytes,
                              bar_full + 8 * st);
                 }
             }
         }
-    } else if (warp == kTcEpiWarps + 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == kTcEpiWarps + 1 || warp == kTcEpiWarps + 2) {
+        // ===================== MMA issuers (one per accumulator) =====================
+        // Warp 9 drives accumulator 0 (query rows 0-127), warp 10 accumulator 1 (rows 128-255): each
+        // waits only for its own four epilogue warps and issues its own two K=16 steps, so the two
+        // row tiles are independent pipelines that merely share the B stages.  A tcgen05 instruction
+        // costs the issuing thread ~70 cycles, and one thread issuing all four MMAs + two commits of
+        // a tile (~470 cycles) sat on the critical release -> MMA -> ready loop of accumulator 1.
         // The whole warp runs the loop so that the two barrier waits of a tile are ONE warp-wide
         // try_wait (lane 1 polls full[stage], the other lanes poll acc_empty[buffer]); lane 0 issues.
-        uint64_t a_desc[2][2];
+        TC_AUX_SETMAXNREG();
+        const int t = warp - (kTcEpiWarps + 1);
+        uint64_t a_desc[2];
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-                a_desc[t][ks] = umma_desc(sbase + kSmemA + t * kTcTileBytes + ks * 256, 128, 512);
+        for (int ks = 0; ks < 2; ++ks) a_desc[ks] = umma_desc(sbase + kSmemA + t * kTcTileBytes + ks * 256, 128, 512);
         const uint64_t b_desc0 = umma_desc(sbase + kSmemB, 128, 512);
+        const uint32_t my_commit = t == 0 ? bar_done0 : bar_done;
         uint32_t it = 0, rbi = 0;
+        unsigned long long chain[2] = {0, 0};   // bring-up only: release->detect, detect->issued
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
             int rblk, sp, tile0;
             const int tiles = unit_of(u, rblk, sp, tile0);
             mbar_wait(bar_a_full, rbi & 1);
-            for (int j = 0; j < tiles; ++j, ++it) {
+            const int sweep = tiles + warm_of(tiles);
+            for (int j = 0; j < sweep; ++j, ++it) {
                 const uint32_t st = it % kTcStages;
                 const uint32_t buf = it & 1;
-                const uint32_t my_bar = (lane == 1) ? bar_full + 8 * st : bar_acc_empty + 8 * buf;
-                const uint32_t my_par = (lane == 1) ? ((it / kTcStages) & 1) : (((it >> 1) & 1) ^ 1);
                 uint32_t spins = 0;
+                const uint32_t my_bar = (lane == 1) ? bar_full + 8 * st : bar_acc_empty + 8 * (buf * 2 + t);
+                const uint32_t my_par = (lane == 1) ? ((it / kTcStages) & 1) : (((it >> 1) & 1) ^ 1);
                 while (!__all_sync(0xffffffffu, mbar_try_wait(my_bar, my_par))) {
                     if (++spins > (1u << 25)) __trap();
                 }
                 tc_fence_after();
+#ifdef MEPOL_BRINGUP
+                const uint32_t ck_detect = (uint32_t)clock64();
+                if (t == 1 && lane == 0 && it >= 2) chain[0] += (uint32_t)(ck_detect - ts_s[(it - 2) & 7]);
+#endif
                 if (lane == 0) {
                     // one K=16 step = two 16-byte k-chunks = 256 bytes further along K
                     const uint64_t bd0 = b_desc0 + (uint64_t)((st * kTcTileBytes) >> 4);
                     const uint64_t bd1 = bd0 + (256 >> 4);
-                    // accumulator 0 is committed on its own: its four epilogue warps start ~190 cycles
-                    // before those of accumulator 1, so the two warps that share an SM sub-partition
-                    // do not run their min trees on the ALU pipe at the same time
-                    const uint32_t d0 = tmem_base + buf * 256;
-                    tc_mma_bf16(d0, a_desc[0][0], bd0, kTcIdesc, 0);
-                    tc_mma_bf16(d0, a_desc[0][1], bd1, kTcIdesc, 1);
-                    tc_commit(bar_done0 + 8 * st);
-                    tc_mma_bf16(d0 + 128, a_desc[1][0], bd0, kTcIdesc, 0);
-                    tc_mma_bf16(d0 + 128, a_desc[1][1], bd1, kTcIdesc, 1);
-                    tc_commit(bar_done + 8 * st);   // commits retire in order: this one also covers the stage
+                    const uint32_t d0 = tmem_base + buf * 256 + t * 128;
+                    tc_mma_f16(d0, a_desc[0], bd0, kTcIdesc, 0);
+                    tc_mma_f16(d0, a_desc[1], bd1, kTcIdesc, 1);
+                    tc_commit(my_commit + 8 * st);
+#ifdef MEPOL_BRINGUP
+                    const uint32_t ck_issued = (uint32_t)clock64();
+                    if (t == 1) {
+                        ts_s[8 + (it & 7)] = ck_issued;
+                        chain[1] += (uint32_t)(ck_issued - ck_detect);
+                    }
+#endif
                 }
                 __syncwarp();
             }
             if (lane == 0) tc_commit(bar_a_empty);   // query tiles reusable once every MMA of the block retired
             __syncwarp();
         }
+#ifdef MEPOL_BRINGUP
+        if (dump && lane == 0 && !kDump && t == 1) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 6, chain[0]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 7, chain[1]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 10, (unsigned long long)it);
+        }
+#endif
     } else if (warp < kTcEpiWarps) {
         // ===================== epilogue: one query row per thread =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
@@ -209,10 +250,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int my_base = rloc * kTcBufStride;
         const float A = glob[G_AMAX], D = glob[G_DELTA_MAX];
         const float INF = __int_as_float(0x7f800000);
-        const uint32_t my_done = t == 0 ? bar_done0 : bar_done;
+        // Loop-invariant addresses are made opaque to the compiler: it otherwise re-derives them from
+        // S2R (tid, cluster CTA id) reads in every tile, a ~60-cycle dependent chain in front of the
+        // TMEM load.
+        uint32_t my_done = t == 0 ? bar_done0 : bar_done;
+        uint32_t tmem_row = tmem_base + lane_base + t * 128;
+        uint32_t acc_empty_addr = bar_acc_empty + 8 * t;
+        asm volatile("mov.u32 %0, %0;\n\tmov.u32 %1, %1;\n\tmov.u32 %2, %2;" : "+r"(my_done), "+r"(tmem_row), "+r"(acc_empty_addr));
         uint32_t it = 0;
         unsigned n_compactions = 0;
         unsigned long long n_cand = 0;
+        long long prof[6] = {0, 0, 0, 0, 0, 0};   // bring-up only: cycles in wait / ld / tree / slow, slow entries, tiles
+        unsigned long long chainE[2] = {0, 0};
         bool next_ready = false;
 
         float *stg = reinterpret_cast<float *>(smem + kSmemStage) + warp * (32 * 33);   // per-warp transpose tile
@@ -296,15 +345,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
             const int rot = kDump ? 0 : (rblk * 2) % tiles;
-            for (int j = 0; j < tiles; ++j, ++it) {
+            const int warm = warm_of(tiles), sweep = tiles + warm;
+            for (int j = 0; j < sweep; ++j, ++it) {
                 int jt = j + rot;
+                if (jt >= tiles) jt -= tiles;
                 if (jt >= tiles) jt -= tiles;
                 jt += tile0;
                 const uint32_t buf = it & 1;
                 const uint32_t st = it % kTcStages;
+                const long long pt0 = TC_PROF_NOW();
                 if (!next_ready) mbar_wait(my_done + 8 * st, (it / kTcStages) & 1);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + lane_base + buf * 256 + t * 128;
+                const long long pt1 = TC_PROF_NOW();
+                const uint32_t tbase = tmem_row + buf * 256;
                 // pull the thread's whole 128-column row into registers and hand the TMEM buffer
                 // back to the MMA issuer at once: the filter below overlaps the next tiles' MMAs
                 float v[4][32];
@@ -317,7 +370,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (epi_mode != 2) tc_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+                if (lane == 0) mbar_arrive(acc_empty_addr + 16 * buf);
+                const long long pt2 = TC_PROF_NOW();
+#ifdef MEPOL_BRINGUP
+                if (warp == 7 && lane == 0) {
+                    ts_s[it & 7] = (uint32_t)pt2;                                  // release of this tile's buffer
+                    chainE[0] += (uint32_t)((uint32_t)pt1 - ts_s[8 + (it & 7)]);   // issued -> seen ready
+                    chainE[1] += (uint32_t)(pt2 - pt1);                            // seen -> loaded + released
+                }
+#endif
+                prof[0] += pt1 - pt0;
+                prof[1] += pt2 - pt1;
+                ++prof[5];
                 if (epi_mode == 1 || epi_mode == 2) continue;   // bring-up timing modes: no filter
                 if (kDump) {
                     if (rblk == 0)
@@ -339,75 +403,62 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     gm[c] = fminf(fmin3(m0, m1, m2), m3);
                 }
                 const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
-                if (__any_sync(0xffffffffu, mm < tau)) {
-                    // Warp-uniform, branch-light slow path.  The 32x32 group (32 rows x 32 columns)
-                    // is transposed through shared memory so that, for every row with a survivor, the
-                    // 32 lanes test its 32 columns at once and append all survivors with one ballot.
+                if (K1 > 0 && j < warm) {
+                    // warm-up tile: the tile minimum is the score of one reference of this tile, so the
+                    // k1 smallest minima bound the k1-th smallest score from above (padding references
+                    // carry a score above every real one and never are a minimum)
+                    topk_insert(mm);
+                    if (live) tau = topk[K1 - 1] + band;
+                    if (j == warm - 1) {
+                        // the sweep proper sees every tile once more: restart the list, keep tau
+#pragma unroll
+                        for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
+                    }
+                    continue;
+                }
+                const long long pt3 = TC_PROF_NOW();
+                prof[2] += pt3 - pt2;
+                if (__any_sync(0xffffffffu, mm < tau) || epi_mode == 3) {
+                    ++prof[4];
+                    // Slow path, per lane and shuffle-free.  Each lane builds the bit mask of its own
+                    // row's survivors in the 32-column group straight from registers, parks the group
+                    // in its private row of the staging tile (registers cannot be indexed by a run-time
+                    // column) and then walks the mask: lanes with survivors run the short loop
+                    // together, the others idle.  No ballot / shuffle chain and no cross-lane
+                    // dependency, so a typical late entry (one survivor in one row) is ~150 cycles.
                     // Invariant: cnt <= kTcSoftCap (32) on entry, a group appends <= 32, buffer = 64.
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        unsigned hit_lanes = __ballot_sync(0xffffffffu, gm[c] < tau);
-                        if (hit_lanes == 0) continue;
+                        if (!(__any_sync(0xffffffffu, gm[c] < tau) || (epi_mode == 3 && c == 0))) continue;
                         const int ref0 = jt * kTcTileRefs + c * 32;
-                        if (__popc(hit_lanes) > 10) {
-                            // Dense case (the first tiles of a row block, before tau has tightened): most
-                            // rows have survivors, so every lane appends its own straight from registers
-                            // (predicated, no per-row loop); tau is refreshed once per group.
-                            const float tau0 = tau;
+                        unsigned mask = 0;
 #pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) {
-                                const bool h = v[c][jj] < tau0 && ref0 + jj < n_ref;
-                                if (h) {
-                                    bufv[my_base + cnt] = v[c][jj];
-                                    bufi[my_base + cnt] = ref0 + jj;
-                                    ++cnt;
-                                }
-                                if (K1 > 0) topk_insert(h ? v[c][jj] : INF);
-                            }
-                            if (K1 > 0) tau = fminf(tau, topk[K1 - 1] + band);
-                            unsigned full = __ballot_sync(0xffffffffu, cnt > kTcSoftCap);
-                            while (full) {
-                                const int L = __ffs(full) - 1;
-                                full &= full - 1;
-                                coop_compact(L, cnt, tau, band, ovf);
-                            }
-                            continue;
-                        }
+                        for (int jj = 0; jj < 32; ++jj) mask |= (v[c][jj] < tau ? 1u : 0u) << jj;
+                        if (ref0 + 32 > n_ref) mask &= ref0 < n_ref ? (1u << (n_ref - ref0)) - 1u : 0u;   // padding columns
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) stg[lane * 33 + jj] = v[c][jj];
-                        __syncwarp();
-                        while (hit_lanes) {
-                            const int L = __ffs(hit_lanes) - 1;
-                            hit_lanes &= hit_lanes - 1;
-                            const float tau_L = __shfl_sync(0xffffffffu, tau, L);
-                            const int cnt_L = __shfl_sync(0xffffffffu, cnt, L);
-                            const int base_L = (warp_row0 + L) * kTcBufStride;
-                            const float x = stg[L * 33 + lane];
-                            const bool h = x < tau_L && ref0 + lane < n_ref;
-                            unsigned hm = __ballot_sync(0xffffffffu, h);
-                            const int n_new = __popc(hm);
-                            if (h) {
-                                const int pos = cnt_L + __popc(hm & ((1u << lane) - 1u));
-                                bufv[base_L + pos] = x;
-                                bufi[base_L + pos] = ref0 + lane;
-                            }
-                            if (lane == L) cnt += n_new;
-                            if (K1 > 0) {
-                                while (hm) {
-                                    const int src = __ffs(hm) - 1;
-                                    hm &= hm - 1;
-                                    const float xv = __shfl_sync(0xffffffffu, x, src);
-                                    topk_insert(lane == L ? xv : INF);
+                        while (mask) {
+                            const int jj = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float x = stg[lane * 33 + jj];
+                            if (x < tau) {                 // tau may have tightened inside this loop
+                                bufv[my_base + cnt] = x;
+                                bufi[my_base + cnt] = ref0 + jj;
+                                ++cnt;
+                                if (K1 > 0) {
+                                    topk_insert(x);
+                                    tau = fminf(tau, topk[K1 > 0 ? K1 - 1 : 0] + band);
                                 }
-                                tau = fminf(tau, topk[K1 - 1] + band);
-                            }
-                            if (cnt_L + n_new > kTcSoftCap) {
-                                __syncwarp();
-                                coop_compact(L, cnt, tau, band, ovf);
                             }
                         }
-                        __syncwarp();
+                        unsigned full = __ballot_sync(0xffffffffu, cnt > kTcSoftCap);
+                        while (full) {
+                            const int L = __ffs(full) - 1;
+                            full &= full - 1;
+                            coop_compact(L, cnt, tau, band, ovf);
+                        }
                     }
+                    prof[3] += TC_PROF_NOW() - pt3;
                 }
             }
             if (!kDump) {
@@ -422,7 +473,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (ovf) {
                         flag[row] = 1;
                         cand_cnt[(size_t)row * n_split + sp] = 0;
-                        if (stats) atomicAdd(stats + 3, 1ULL);   // rows whose bf16 band overflowed
+                        if (stats) atomicAdd(stats + 3, 1ULL);   // rows whose fp16 band overflowed
                     } else {
                         cand_cnt[(size_t)row * n_split + sp] = cnt;
                         n_cand += cnt;
@@ -438,6 +489,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 __syncwarp();
             }
         }
+#ifdef MEPOL_BRINGUP
+        if (!kDump && dump && lane == 0)
+            for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + i, (unsigned long long)prof[i]);
+        if (!kDump && dump && warp == 7 && lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 8, chainE[0]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 9, chainE[1]);
+        }
+#endif
         if (!kDump && stats) {
             n_cand = (unsigned long long)warp_sum((double)n_cand);
             unsigned long long nc = (unsigned long long)warp_sum((double)n_compactions);
@@ -446,7 +505,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 atomicAdd(stats + 2, nc);
             }
         }
+    } else {
+        TC_AUX_SETMAXNREG();   // (setmaxnreg is warpgroup-wide)
     }
+#undef TC_AUX_SETMAXNREG
 
     tc_fence_before();
     __syncthreads();
@@ -460,7 +522,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     // k+1 = 5 (every shipped MEPOL config but GridWorld) gets the register-resident running top-k1
     auto kern = p.k1 == 5 ? knn_prune_tc_kernel<false, 5> : knn_prune_tc_kernel<false, 0>;
-    MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    const int smem_bytes = kSmemTotal;
+    MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int n_row_blocks = (int)(p.n_q_pad / kTcRows);
     const int n_ref_tiles = (int)(p.n_ref_pad / kTcTileRefs);
     int grid = device_sm_count();
@@ -473,10 +536,35 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
 #else
     const int epi_mode = 0;
 #endif
-    kern<<<grid, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
-                                               n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, nullptr,
-                                               epi_mode, n_full_blocks, p.tc_tail_split, p.n_split);
+    int warm_tiles = kTcWarmTiles;
+    if (const char *wt = getenv("MEPOL_TC_WARM_TILES")) warm_tiles = atoi(wt);   // tuning aid; any value >= 0 is exact
+    if (warm_tiles < 0) warm_tiles = 0;
+    float *prof_dev = nullptr;
+#ifdef MEPOL_BRINGUP
+    static unsigned long long *prof_buf = nullptr;
+    if (getenv("MEPOL_TC_PROF")) {
+        if (!prof_buf) cudaMalloc(&prof_buf, 128);
+        cudaMemsetAsync(prof_buf, 0, 128, st);
+        prof_dev = reinterpret_cast<float *>(prof_buf);
+    }
+#endif
+    kern<<<grid, kTcThreads, smem_bytes, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
+                                               n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, prof_dev,
+                                               epi_mode, n_full_blocks, p.tc_tail_split, p.n_split, warm_tiles);
     MEPOL_CUDA_CHECK(cudaGetLastError());
+#ifdef MEPOL_BRINGUP
+    if (prof_dev) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const double w = (double)grid * kTcEpiWarps, tl = (double)h[5] / w;
+        fprintf(stderr, "[tc prof] per warp: tiles %.0f  cycles/tile: wait %.1f ld %.1f tree %.1f slow %.1f  slow entries/tile %.4f  cycles/entry %.0f\n",
+                tl, h[0] / w / tl, h[1] / w / tl, h[2] / w / tl, h[3] / w / tl, (double)h[4] / h[5], h[4] ? (double)h[3] / h[4] : 0.0);
+        if (h[10])
+            fprintf(stderr, "[tc chain] cycles/tile: release->issuer detect %.1f  detect->issued %.1f  issued->epilogue sees ready %.1f  seen->loaded+released %.1f\n",
+                    (double)h[6] / h[10], (double)h[7] / h[10], (double)h[8] / h[10], (double)h[9] / h[10]);
+    }
+#endif
     return MEPOL_OK;
 }
 
@@ -485,7 +573,7 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
     auto kern = knn_prune_tc_kernel<true, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
-                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1);
+                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1, 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

@@ -1,14 +1,14 @@
 // PTX wrappers shared by the tcgen05 pruner variants (knn_tc.cu, knn_tc16.cu): mbarrier, bulk copy,
 // tcgen05 mma / ld / commit / fences, UMMA descriptors and the proven error band.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "knn_internal.cuh"
 
 namespace mepol {
 
 constexpr int kTcTileRefs = 128;
-constexpr int kTcTileBytes = 128 * kTcKPad * 2;  // 8192 B: one 128-row x 32-col bf16 operand tile
+constexpr int kTcTileBytes = 128 * kTcKPad * 2;  // 8192 B: one 128-row x 32-col fp16 operand tile
 constexpr int kTcTmemCols = 512;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -63,7 +63,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -112,9 +112,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;
     return d;
 }
-// Instruction descriptor (InstrDescriptor): c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// Instruction descriptor (InstrDescriptor): c_format F32 (bit 4), a/b format F16 (0 in bits 7-9 / 10-12; BF16 would be 1),
 // K-major A and B, N>>3 at bit 17, M>>4 at bit 24.
-constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcTileRefs >> 3) << 17) |
+constexpr uint32_t kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTcTileRefs >> 3) << 17) |
                               ((uint32_t)(128 >> 4) << 24);
 
 // Error band of the tensor-core score for one query row (DESIGN.md "pruning band"):

@@ -1,6 +1,6 @@
 """Bring-up diagnostics for the tcgen05 pruner (run on the B200 box; the MEPOL_TC_EPI_MODE timing
 switch needs a library built with -DMEPOL_BRINGUP: MEPOL_NVCC_EXTRA=-DMEPOL_BRINGUP python -m mepol_b200.build --force):
-   python scripts/tc_bringup.py dump      # raw accumulator tile vs a numpy emulation of the bf16 operands
+   python scripts/tc_bringup.py dump      # raw accumulator tile vs a numpy emulation of the fp16 operands
    python scripts/tc_bringup.py knn N     # TC search vs SIMT search (indices must be identical), timing
 """
 import ctypes
@@ -19,12 +19,14 @@ from mepol_b200 import _lib
 def expected_scores(x, nq=256, nr=128):
     xd = torch.from_numpy(x).double()
     mean = (xd.sum(0) / x.shape[0]).float().double()
-    xc = xd - mean
-    xb = xc.float().to(torch.bfloat16).double()           # (double rounding differs from the kernel ~never)
+    ext = torch.maximum(xd.max(0).values - mean, mean - xd.min(0).values)
+    sigma = 2.0 ** np.floor(np.log2(128.0 / float(ext.pow(2).sum().sqrt())))
+    xc = (xd - mean) * sigma
+    xb = xc.to(torch.float16).double()
     n2 = (xc * xc).sum(1)
-    h = n2.float().to(torch.bfloat16).double()
-    m = (n2 - h).float().to(torch.bfloat16).double()
-    l = (n2 - h - m).float().to(torch.bfloat16).double()
+    h = n2.to(torch.float16).double()
+    m = (n2 - h).to(torch.float16).double()
+    l = (n2 - h - m).to(torch.float16).double()
     nsum = h + m + l
     q, r = xb[:nq], xb[:nr]
     return (nsum[:nr][None, :] - 2.0 * (q @ r.T)).numpy(), n2.numpy()

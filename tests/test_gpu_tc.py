@@ -1,5 +1,5 @@
 """GPU tests specific to the tcgen05 pruner: the raw tensor-core score tile against a float64
-emulation of the bf16 operands, and bit-identity of the full search with the SIMT path (both are
+emulation of the fp16 operands, and bit-identity of the full search with the SIMT path (both are
 exact, so they must agree on every index and every distance)."""
 import numpy as np
 import pytest
@@ -9,19 +9,23 @@ pytestmark = pytest.mark.gpu
 
 import mepol_b200
 from mepol_b200 import _lib
+from conftest import assert_knn_matches
 
 
 def _expected_scores(x, nq=256, nr=128):
-    """Mirror of knn_prep.cu's packing: centre with the float32-rounded mean, round to bf16, split
-    ||y'||^2 over three bf16 terms; D = sum(n_hi, n_mid, n_lo) - 2 x~.y~ in float64."""
+    """Mirror of knn_prep.cu's packing: centre with the float32-rounded mean, scale by the power of
+    two that brings the column-extent bound of the max norm under 128, round to fp16, split ||y'||^2
+    over three fp16 terms; D = sum(n_hi, n_mid, n_lo) - 2 x~.y~ in float64."""
     xd = torch.from_numpy(x).double()
     mean = (xd.sum(0) / x.shape[0]).float().double()
-    xc = xd - mean
-    xb = xc.float().to(torch.bfloat16).double()
+    ext = torch.maximum(xd.max(0).values - mean, mean - xd.min(0).values)
+    sigma = 2.0 ** np.floor(np.log2(128.0 / float(ext.pow(2).sum().sqrt())))
+    xc = (xd - mean) * sigma
+    xb = xc.to(torch.float16).double()
     n2 = (xc * xc).sum(1)
-    h = n2.float().to(torch.bfloat16).double()
-    m = (n2 - h).float().to(torch.bfloat16).double()
-    l = (n2 - h - m).float().to(torch.bfloat16).double()
+    h = n2.to(torch.float16).double()
+    m = (n2 - h).to(torch.float16).double()
+    l = (n2 - h - m).to(torch.float16).double()
     return ((h + m + l)[:nr][None, :] - 2.0 * (xb[:nq] @ xb[:nr].T)).numpy()
 
 
@@ -39,7 +43,7 @@ def test_tensor_core_score_tile(d):
     got = out.cpu().numpy().astype(np.float64)
     exp = _expected_scores(x)
     assert not np.isnan(got).any()
-    # fp32 accumulation of 32 exact bf16 products: a few ulp of the largest term
+    # fp32 accumulation of 32 exact fp16 products: a few ulp of the largest term
     assert np.max(np.abs(got - exp)) < 1e-4 * max(1.0, np.abs(exp).max())
 
 
@@ -66,7 +70,7 @@ def test_tc_rejects_unsupported_shapes():
 
 
 def test_tc_offset_clustered_data_uses_band_and_fallback_correctly():
-    """Tight clusters far from the origin: after centring the bf16 band is wide relative to the
+    """Tight clusters far from the origin: after centring the fp16 band is wide relative to the
     neighbour gaps, so many rows overflow into the exact fallback -- results must still be exact."""
     from oracle import knn_oracle
     rng = np.random.default_rng(8)
@@ -76,3 +80,31 @@ def test_tc_offset_clustered_data_uses_band_and_fallback_correctly():
     res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), 5, algo=_lib.KNN_TC)
     np.testing.assert_array_equal(res.indices.cpu().numpy(), ref_i)
     np.testing.assert_allclose(res.distances.cpu().numpy(), ref_d, rtol=1e-12)
+
+
+def test_tc_queries_outside_fp16_range_take_the_exact_fallback():
+    """Queries far outside the fitted set's extent cannot be represented in the scaled fp16 operand;
+    they get an infinite band, overflow, and are answered by the exact fallback."""
+    from oracle import knn_oracle
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((6000, 29)).astype(np.float32)
+    q = rng.standard_normal((300, 29)).astype(np.float32)
+    q[:7] *= 1e7
+    q[7] += 3e5
+    res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), 5, queries=torch.from_numpy(q).cuda(), algo=_lib.KNN_TC)
+    ref_d, ref_i = knn_oracle.knn_c(x, 5, queries=q, mode="kd_tree")
+    assert res.stats_dict()["tc_overflow_rows"] >= 8
+    assert_knn_matches(res.distances.cpu().numpy(), res.indices.cpu().numpy(), ref_d, ref_i, x, queries=q)
+
+
+@pytest.mark.parametrize("scale", [1e-20, 1e-3, 1e4, 1e15])
+def test_tc_is_scale_invariant(scale):
+    """The power-of-two operand scaling keeps the fp16 pruner usable at any data magnitude."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((20000, 29)) * scale).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    a = mepol_b200.knn_device(xt, 5, algo=_lib.KNN_SIMT)
+    b = mepol_b200.knn_device(xt, 5, algo=_lib.KNN_TC)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+    assert b.stats_dict()["tc_overflow_rows"] == 0
