@@ -403,7 +403,7 @@ def run_ours(args):
     launches_per_step = 11 + 6 + 3
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "bf16",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "f16",
             "data": "synthetic",
             "config": {"workload": f"synthetic sweep N={n} d={d} k={k} L={args.traj_len} (BASELINE.json configs[4])",
                        "algo": args.algo, "parallelism": f"query rows sharded x{world}, refs all-gathered (NCCL)",

@@ -14,18 +14,26 @@
 // threshold, and a rare slow path that appends survivors to the row's candidate buffer.
 // Exactness comes from the proven error band (tc_band) and the fp64 re-rank, never from fp16.
 //
+// The operands are fp16 (not bf16): knn_prep.cu scales the centred data by a power of two so that
+// every fitted row norm is <= 128, which keeps -2y~ and ||y'||^2 inside fp16's range and makes the
+// band ~8x tighter than bf16's (5.3 instead of 8.5 candidates per row at N = 1M, d = 29).
+//
 // CTA = 256 query rows (two M=128 accumulators) x a stream of 128-reference B tiles.
 //   warp 8      bulk-copy producer (cp.async.bulk -> smem, mbarrier complete_tx), 4-stage ring
-//   warp 9      TMEM allocator + tcgen05.mma issuer (cta_group::1, M128 N128 K16, 4 per tile)
+//   warp 9      TMEM allocator + tcgen05.mma issuer of accumulator 0 (cta_group::1, M128 N128 K16 x2)
+//   warp 10     tcgen05.mma issuer of accumulator 1
 //   warps 0-7   epilogue: warp w owns TMEM lanes 32*(w%4).. of accumulator w/4, one row per thread
 // TMEM: 2 buffers x 2 accumulators x 128 columns = 512 columns (all of it).  The epilogue pulls a
 // tile into registers and releases the TMEM buffer before filtering, so the MMA of tile j+1/j+2
 // overlaps the filter of tile j.  Persistent grid (one CTA per SM) over row blocks.
 //
-// Measured on B200 (profiles/): with K = 32 the tensor pipe needs only 256 cycles per tile, so the
-// kernel is bound by fixed per-tile latencies (mbarrier try_wait ~220 cycles even when already
-// complete, tcgen05.ld ~300, tcgen05.mma issue ~70 each), not by the MMA; the structure below
-// minimises the number of serial long-latency operations per tile in every role.
+// Measured on B200 (profiles/r01_tc_pipeline_notes.md): with K = 32 the tensor pipe needs only 256
+// cycles per tile; the kernel is bound by two serial loops of fixed latencies that are both ~870
+// cycles per tile -- per buffer: release -> issuer sees it (~390) -> two MMAs + commit issued (~320)
+// -> MMA retires -> epilogue's barrier query (~200) -> tcgen05.ld (~160) -> release; per epilogue
+// warp: query + load + min tree (~270) + survivor path (~70 average) + loop (~180).  An mbarrier
+// query costs ~200 cycles even when the phase has completed; TMEM (4 fp32 accumulators) caps the
+// depth at two buffers.  The structure below keeps every role's serial chain per tile short.
 //
 // Operand tiles are pre-arranged in global memory by knn_prep.cu in the UMMA canonical K-major
 // no-swizzle order (8x16-byte core matrices, 128 B each): a 128-row x 32-col tile is 8 KB
@@ -401,6 +409,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const float m0 = fmin3(m[0], m[1], m[2]), m1 = fmin3(m[3], m[4], m[5]);
                     const float m2 = fmin3(m[6], m[7], m[8]), m3 = fminf(m[9], m[10]);
                     gm[c] = fminf(fmin3(m0, m1, m2), m3);
+                    if (c == 1 && !next_ready) {
+                        // second probe of the next tile's barrier, anchored inside the min tree: the
+                        // first one (under the TMEM load) is usually a little too early, and the
+                        // blocking wait at the top of the loop costs ~200 cycles even when complete
+                        const uint32_t st1 = (it + 1) % kTcStages;
+                        next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + 1) / kTcStages) & 1, gm[c]);
+                    }
                 }
                 const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
                 if (K1 > 0 && j < warm) {

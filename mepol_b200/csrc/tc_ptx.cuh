@@ -46,6 +46,20 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// the same probe, scheduled after `dep` has been computed (anchors it inside a block of arithmetic
+// whose latency then hides the ~200-cycle round trip of the query)
+__device__ __forceinline__ bool mbar_test_wait_after(uint32_t bar, uint32_t parity, float dep) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\t"
+        "mov.f32 t, %3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "f"(dep)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (clean launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
