@@ -6,6 +6,10 @@
 
 namespace mepol {
 
+constexpr int kTcAutoMinDim = 4;        // AUTO picks the tensor-core pruner for d >= this ...
+constexpr int64_t kTcAutoMinRefs = 512;   // ... and at least this many fitted rows
+
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -49,11 +53,13 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
                   k1, (long long)n_ref);
     MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC, MEPOL_E_INVALID,
                   "knn: unknown algo %d", algo);
-    // AUTO: tensor cores pay off for wide particles and large batches; for d < 16 (the regime where
-    // sklearn itself switches to a kd-tree, neighbors/_base.py:615-626) the fp16 band is too coarse
-    // for the tiny neighbour radii and the fp32 SIMT pruner is both exact-band-tight and cheap.
+    // AUTO: the tensor-core pruner wins from d = 4 up (2.3-5x over the SIMT pruner at N = 10k-50k on
+    // gaussian, uniform and trajectory-like data, profiles/r01_tc_lowdim.md).  For d <= 3 the
+    // neighbour radii are so small next to the row norms that the fp16 band passes too many
+    // candidates (rows overflow into the exact fallback); there the fp32 SIMT pruner is both
+    // band-tight and cheap.  Either way the result is exact.
     if (algo == MEPOL_KNN_AUTO)
-        algo = (tc_supported(d, k1) && n_ref >= 4096 && d >= 16) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
+        algo = (tc_supported(d, k1) && n_ref >= kTcAutoMinRefs && d >= kTcAutoMinDim) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
     if (algo == MEPOL_KNN_TC && !tc_supported(d, k1)) {
         set_error("knn: tensor-core pruner does not support d=%d k1=%d", d, k1);
         return MEPOL_E_UNSUPPORTED;
