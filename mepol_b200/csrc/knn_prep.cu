@@ -56,18 +56,36 @@ __global__ void __launch_bounds__(kMeanThreadsX *kMeanThreadsY)
     }
 }
 
-__global__ void col_mean_final_kernel(const double *__restrict__ partial, int n_blocks, int64_t n, int d,
-                                      double *__restrict__ mean, float *__restrict__ glob) {
+constexpr int kMeanFinalY = 16;
+
+__global__ void __launch_bounds__(64 * kMeanFinalY)
+    col_mean_final_kernel(const double *__restrict__ partial, int n_blocks, int64_t n, int d,
+                          double *__restrict__ mean, float *__restrict__ glob) {
     __shared__ double r2[64];
-    const int c = threadIdx.x;
+    __shared__ double ssum[kMeanFinalY][64], slo[kMeanFinalY][64], shi[kMeanFinalY][64];
+    const int c = threadIdx.x, y = threadIdx.y;
+    {   // kMeanFinalY interleaved chains per column, combined in a fixed order (deterministic)
+        double t = 0.0, lo = 1e300, hi = -1e300;
+        if (c < d)
+            for (int b = y; b < n_blocks; b += kMeanFinalY) {
+                const double *pb = partial + (int64_t)b * (3 * MEPOL_MAX_DIM);
+                t += pb[c];
+                lo = fmin(lo, pb[MEPOL_MAX_DIM + c]);
+                hi = fmax(hi, pb[2 * MEPOL_MAX_DIM + c]);
+            }
+        ssum[y][c] = t;
+        slo[y][c] = lo;
+        shi[y][c] = hi;
+    }
+    __syncthreads();
+    if (y != 0) return;
     double ext = 0.0;
     if (c < d) {
         double t = 0.0, lo = 1e300, hi = -1e300;
-        for (int b = 0; b < n_blocks; ++b) {           // fixed order
-            const double *pb = partial + (int64_t)b * (3 * MEPOL_MAX_DIM);
-            t += pb[c];
-            lo = fmin(lo, pb[MEPOL_MAX_DIM + c]);
-            hi = fmax(hi, pb[2 * MEPOL_MAX_DIM + c]);
+        for (int i = 0; i < kMeanFinalY; ++i) {
+            t += ssum[i][c];
+            lo = fmin(lo, slo[i][c]);
+            hi = fmax(hi, shi[i][c]);
         }
         // The mean only has to be the SAME value for queries and references; rounding it to
         // float keeps x - mean exactly representable in float64 for every float32 input.
@@ -76,7 +94,8 @@ __global__ void col_mean_final_kernel(const double *__restrict__ partial, int n_
         ext = fmax(hi - m, m - lo);
     }
     r2[c] = ext * ext;
-    __syncthreads();
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");      // the 64 threads of row y == 0 (two warps)
     if (c == 0) {
         // Power-of-two scale sigma with sigma * max_row ||x - mean|| <= kTcScaledNormMax, from the
         // per-column extents (an upper bound of the max norm).  Scaling by 2^e is exact, so the
@@ -99,7 +118,7 @@ __global__ void col_mean_final_kernel(const double *__restrict__ partial, int n_
 int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cudaStream_t st) {
     dim3 blk(kMeanThreadsX, kMeanThreadsY);
     col_sum_partial_kernel<<<p.mean_blocks, blk, 0, st>>>(ref, n_ref, d, p.mean_partial);
-    col_mean_final_kernel<<<1, 64, 0, st>>>(p.mean_partial, p.mean_blocks, n_ref, d, p.mean, p.glob);
+    col_mean_final_kernel<<<1, dim3(64, kMeanFinalY), 0, st>>>(p.mean_partial, p.mean_blocks, n_ref, d, p.mean, p.glob);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
