@@ -28,9 +28,10 @@ extern "C" {
 #define MEPOL_E_CUDA (-3)      /* CUDA runtime error / no device */
 #define MEPOL_E_UNSUPPORTED (-4)
 
-#define MEPOL_KNN_AUTO 0 /* tensor-core pruner when the shape allows it, else SIMT */
+#define MEPOL_KNN_AUTO 0 /* grid search for d <= 3, tensor-core pruner for 4 <= d <= 29 and k1 <= 12, else SIMT */
 #define MEPOL_KNN_SIMT 1 /* fp32 SIMT pruner + fp64 re-rank (any d <= 64, k1 <= 60) */
-#define MEPOL_KNN_TC 2   /* tcgen05 bf16 pruner + fp64 re-rank (d <= 61, k1 <= 12) */
+#define MEPOL_KNN_TC 2   /* tcgen05 fp16 pruner + fp64 re-rank (d <= 29, k1 <= 12) */
+#define MEPOL_KNN_GRID 3 /* uniform-grid exact search in fp64 (d <= 3, k1 <= 60): the kd-tree regime */
 
 #define MEPOL_MAX_DIM 64
 #define MEPOL_MAX_K1 60

@@ -9,7 +9,7 @@ All compute runs in libmepol_b200.so (hand-written CUDA behind the C ABI of incl
 there is no CPU fallback.
 """
 from . import _lib
-from ._lib import KNN_AUTO, KNN_SIMT, KNN_TC, MepolError
+from ._lib import KNN_AUTO, KNN_GRID, KNN_SIMT, KNN_TC, MepolError
 from .knn import KnnResult, knn, knn_device, knn_host_c
 from .entropy import (IWEntropyFunction, SearchHandle, compute_entropy, compute_importance_weights,
                       compute_kl, configure, gaussian_log_p, iw_entropy, policy_update, traj_offsets)
@@ -17,7 +17,7 @@ from .dropin import (collect_particles, collect_particles_and_compute_knn, insta
                      uninstall)
 
 __all__ = [
-    "KNN_AUTO", "KNN_SIMT", "KNN_TC", "MepolError", "KnnResult", "knn", "knn_device", "knn_host_c",
+    "KNN_AUTO", "KNN_GRID", "KNN_SIMT", "KNN_TC", "MepolError", "KnnResult", "knn", "knn_device", "knn_host_c",
     "IWEntropyFunction", "SearchHandle", "compute_entropy", "compute_importance_weights", "compute_kl",
     "configure", "gaussian_log_p", "iw_entropy", "policy_update", "traj_offsets", "collect_particles",
     "collect_particles_and_compute_knn", "install", "search_particles", "uninstall",

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmepol_b200.so")
 
-KNN_AUTO, KNN_SIMT, KNN_TC = 0, 1, 2
+KNN_AUTO, KNN_SIMT, KNN_TC, KNN_GRID = 0, 1, 2, 3
 KNN_NSTATS = 8
 MAX_DIM, MAX_K1 = 64, 60
 

@@ -51,15 +51,24 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
     // mirrors sklearn's ValueError "Expected n_neighbors <= n_samples_fit" (neighbors/_base.py:834)
     MEPOL_REQUIRE(k1 <= n_ref, MEPOL_E_INVALID, "knn: Expected n_neighbors <= n_samples_fit, got k1=%d n_ref=%lld",
                   k1, (long long)n_ref);
-    MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC, MEPOL_E_INVALID,
-                  "knn: unknown algo %d", algo);
+    MEPOL_REQUIRE(algo == MEPOL_KNN_AUTO || algo == MEPOL_KNN_SIMT || algo == MEPOL_KNN_TC || algo == MEPOL_KNN_GRID,
+                  MEPOL_E_INVALID, "knn: unknown algo %d", algo);
     // AUTO: the tensor-core pruner wins from d = 4 up (2.3-5x over the SIMT pruner at N = 10k-50k on
     // gaussian, uniform and trajectory-like data, profiles/r01_tc_lowdim.md).  For d <= 3 the
     // neighbour radii are so small next to the row norms that the fp16 band passes too many
     // candidates (rows overflow into the exact fallback); there the fp32 SIMT pruner is both
     // band-tight and cheap.  Either way the result is exact.
-    if (algo == MEPOL_KNN_AUTO)
-        algo = (tc_supported(d, k1) && n_ref >= kTcAutoMinRefs && d >= kTcAutoMinDim) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
+    // d <= 3 is the reference's kd-tree regime: the uniform-grid search is O(N k) instead of O(N^2).
+    if (algo == MEPOL_KNN_AUTO) {
+        if (grid_supported(d, k1))
+            algo = MEPOL_KNN_GRID;
+        else
+            algo = (tc_supported(d, k1) && n_ref >= kTcAutoMinRefs && d >= kTcAutoMinDim) ? MEPOL_KNN_TC : MEPOL_KNN_SIMT;
+    }
+    if (algo == MEPOL_KNN_GRID && !grid_supported(d, k1)) {
+        set_error("knn: grid search does not support d=%d k1=%d", d, k1);
+        return MEPOL_E_UNSUPPORTED;
+    }
     if (algo == MEPOL_KNN_TC && !tc_supported(d, k1)) {
         set_error("knn: tensor-core pruner does not support d=%d k1=%d", d, k1);
         return MEPOL_E_UNSUPPORTED;
@@ -85,6 +94,14 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         if (max_split > ref_tiles / 4) max_split = ref_tiles / 4;
         if (max_split < 1) max_split = 1;
         p.n_split = (int)(want < 1 ? 1 : (want > max_split ? max_split : want));
+    } else if (algo == MEPOL_KNN_GRID) {
+        p.rows_per_thread = 1;
+        p.rows_per_cta = 256;
+        p.n_split = 1;
+        p.cap = 1;    // no candidate lists: the grid kernel writes the final rows itself
+        p.grid_g = grid_cells_per_dim(n_ref, d, k1);
+        p.grid_cells = p.grid_g;
+        for (int c = 1; c < d; ++c) p.grid_cells *= p.grid_g;
     } else {
         p.rows_per_thread = 1;
         p.rows_per_cta = 256;
@@ -131,6 +148,13 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rb = c.take<uint16_t>((size_t)p.n_ref_pad * kTcKPad);
         p.qb = c.take<uint16_t>((size_t)p.n_q_pad * kTcKPad);
         p.q_delta = c.take<float>((size_t)n_q);
+    }
+    if (algo == MEPOL_KNN_GRID) {
+        p.grid_pts = c.take<float>((size_t)n_ref * 4);
+        p.grid_par = c.take<unsigned char>(grid_par_bytes());
+        p.grid_start = c.take<int32_t>((size_t)p.grid_cells + 1);
+        p.grid_cursor = c.take<int32_t>((size_t)p.grid_cells);
+        p.grid_cell_of = c.take<int32_t>((size_t)n_ref);
     }
     p.cand = c.take<int32_t>((size_t)n_q * p.n_split * p.cap);
     p.cand_cnt = c.take<int32_t>((size_t)n_q * p.n_split);
@@ -225,6 +249,18 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         MEPOL_CUDA_CHECK(cudaMemsetAsync(p.cand_cnt, 0, sizeof(int32_t) * (size_t)n_q * p.n_split, st));
     MEPOL_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, sizeof(unsigned long long) * MEPOL_KNN_NSTATS, st));
     if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
+    if (p.algo == MEPOL_KNN_GRID) {
+        // no pruning pass: the grid kernel produces the final rows (rows it cannot fill go to the fallback)
+        prof_record(0, st);
+        rc = launch_grid_search(ref, q, p, idx_out, dist_out, rk_out, st);
+        prof_record(1, st);
+        if (rc != MEPOL_OK) return rc;
+        if ((rc = launch_exact_fallback(ref, q, p, idx_out, dist_out, rk_out, st)) != MEPOL_OK) return rc;
+        if (stats)
+            MEPOL_CUDA_CHECK(cudaMemcpyAsync(stats, p.stats, sizeof(int64_t) * MEPOL_KNN_NSTATS,
+                                             cudaMemcpyDeviceToDevice, st));
+        return MEPOL_OK;
+    }
     if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
     if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     prof_record(0, st);

@@ -45,6 +45,10 @@ struct KnnPlan {
     uint16_t *rb, *qb;
     float *q_delta;
     int64_t n_ref_pad, n_q_pad;
+    // uniform-grid search (d <= 3, knn_grid.cu)
+    int grid_g, grid_cells;
+    void *grid_pts, *grid_par;
+    int32_t *grid_start, *grid_cursor, *grid_cell_of;
     // parallel exact fallback scratch
     int fb_max_rows;
     int32_t *fb_list, *fb_part_i;
@@ -66,6 +70,12 @@ int launch_rescue_simt(const KnnPlan &p, cudaStream_t st);
 bool tc_supported(int d, int k1);
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st);
 int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st);
+// knn_grid.cu
+bool grid_supported(int d, int k1);
+int grid_cells_per_dim(int64_t n_ref, int d, int k1);
+size_t grid_par_bytes();
+int launch_grid_search(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out, double *dist_out,
+                       double *rk_out, cudaStream_t st);
 // knn_rerank.cu
 int launch_rerank(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out,
                   double *dist_out, double *rk_out, cudaStream_t st);

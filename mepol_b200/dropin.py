@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import entropy as _entropy
-from .knn import knn_device
+from .knn import knn_device, to_host
 
 _ORIGINALS = {}
 _REPLACED = ("collect_particles_and_compute_knn", "compute_importance_weights", "compute_entropy",
@@ -66,9 +66,9 @@ def search_particles(next_states, k):
         raise ValueError("Input contains NaN or infinity")
     dev = _entropy._device()
     xt = torch.from_numpy(x).pin_memory().to(dev, non_blocking=True)
-    res = knn_device(xt, k + 1)
-    distances = res.distances.cpu()
-    indices = res.indices.to(torch.int64).cpu()
+    with torch.cuda.device(dev):
+        res = knn_device(xt, k + 1)
+        distances, indices = to_host(res)
     handle = _entropy.SearchHandle(res.indices, res.rk, k + 1)
     _entropy.attach_handle(indices, handle)
     return distances, indices, handle
