@@ -212,6 +212,7 @@ class _Batch:
         self.n_traj = int(num_traj)
         self.action_dim = int(a.shape[-1])
         self.behav_cache = None     # (param fingerprint, logp_b)
+        self.pinned = {}            # pinned host mirrors for async device->host copies
 
 
 _batches = {}
@@ -260,13 +261,59 @@ def _fingerprint(policy):
     return tuple((p.data_ptr(), p._version) for p in policy.parameters())
 
 
+_BURN_FAST = None
+_BURN_POOL = None
+
+
+def _burn_fast_ok():
+    """torch's CPU normal_ on a contiguous float64 tensor of n >= 16 elements draws n 64-bit words from
+    the generator (+16 when n % 16 != 0: the tail block is redrawn) and nothing else, so the generator
+    can be advanced by the same amount without the Box-Muller arithmetic (int64 random_() draws one
+    64-bit word per element: 2.5x cheaper).  That is an implementation detail of the installed torch:
+    it is CHECKED here once, on a private generator, and the literal randn calls are used if it fails."""
+    global _BURN_FAST
+    if _BURN_FAST is None:
+        ok = True
+        for n in (4000, 37 * 3, 16):
+            g1, g2 = torch.Generator(), torch.Generator()
+            g1.manual_seed(20260101)
+            g2.manual_seed(20260101)
+            torch.randn(n, dtype=torch.float64, generator=g1)
+            torch.empty(n + (16 if n % 16 else 0), dtype=torch.int64).random_(generator=g2)
+            ok = ok and torch.equal(g1.get_state(), g2.get_state())
+        _BURN_FAST = ok
+    return _BURN_FAST
+
+
 def _burn_rng(batch, calls=2):
     """Q7: every reference get_log_p call draws randn(len, A) from the global CPU generator
     (policy.py:59), target first then behavioural, trajectory by trajectory (mepol.py:127-128)."""
-    if _config["burn_rng"]:
-        for l in batch.lens:
-            for _ in range(calls):
-                torch.randn((l, batch.action_dim), dtype=torch.float64)
+    if not _config["burn_rng"]:
+        return
+    sizes = [l * batch.action_dim for l in batch.lens]
+    if min(sizes) >= 16 and _burn_fast_ok():
+        total = calls * sum(n + (16 if n % 16 else 0) for n in sizes)
+        buf = batch.pinned.get("burn")
+        if buf is None or buf.numel() != total:
+            buf = torch.empty(total, dtype=torch.int64)
+            batch.pinned["burn"] = buf
+        buf.random_()
+        return
+    for l in batch.lens:
+        for _ in range(calls):
+            torch.randn((l, batch.action_dim), dtype=torch.float64)
+
+
+def _burn_rng_async(batch, calls=2):
+    """The burn runs on a helper thread (torch releases the GIL inside the generator loop) while the
+    caller enqueues the step's device work; nothing else touches the CPU generator meanwhile."""
+    global _BURN_POOL
+    if not _config["burn_rng"]:
+        return None
+    if _BURN_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _BURN_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mepol-burn")
+    return _BURN_POOL.submit(_burn_rng, batch, calls)
 
 
 def _behav_logp(behavioral_policy, batch):
@@ -280,29 +327,63 @@ def _behav_logp(behavioral_policy, batch):
     return lb
 
 
+def _pinned(batch, name, like):
+    """Per-batch pinned host mirrors (allocated once): async device->host copies need them."""
+    buf = batch.pinned.get(name)
+    if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+        buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+        batch.pinned[name] = buf
+    return buf
+
+
 class _EntropyBridge(torch.autograd.Function):
-    """CPU parameters -> (entropy, kl_raw, n_bad) CPU scalars, everything in between on the GPU."""
+    """CPU parameters -> (entropy, kl_raw, n_bad) CPU scalars, everything in between on the GPU.
+
+    The whole device side of a step -- forward, and when a gradient will be wanted also the backward
+    for dH = 1 plus the device->host copies -- is ENQUEUED first; the Q7 random-number burn (2.5 ms of
+    CPU work at Ant's N = 10000, more than all the GPU work of the step) then runs on the host while
+    the GPU works, and one stream synchronisation ends the call.  backward() only scales the stored
+    gradients by the incoming dH (the loss is -H)."""
 
     @staticmethod
     def forward(ctx, pack, *cpu_params):
         target_policy, lb, batch, handle, k, ns, G, B, eps = pack
         dev, dt = batch.states.device, batch.states.dtype
         want_grad = any(ctx.needs_input_grad[1:])
-        gp = [p.detach().to(device=dev, dtype=dt).requires_grad_(want_grad) for p in cpu_params]
+        burn = _burn_rng_async(batch)                  # host-side work that overlaps everything below
+        gp = [p.detach().to(device=dev, dtype=dt, non_blocking=True).requires_grad_(want_grad) for p in cpu_params]
+        pinned_grads = None
         with torch.set_grad_enabled(want_grad):
             lt = gaussian_log_p(target_policy, gp, batch.states, batch.actions)
             H, kl_raw, n_bad = iw_entropy(lt, lb, handle, batch.traj_off, batch.n_traj, k, ns, G, B, eps)
-        ctx.gp, ctx.H = gp, (H if want_grad else None)
-        ctx.dtypes = [p.dtype for p in cpu_params]
-        out = torch.stack([H.detach(), kl_raw, n_bad]).cpu()
-        ent, klv, bad = out[0].clone(), out[1].clone(), out[2].clone()
+        if want_grad:
+            grads = torch.autograd.grad(H, gp, allow_unused=True)
+            pinned_grads = []
+            for i, (g, p) in enumerate(zip(grads, cpu_params)):
+                if g is None:
+                    pinned_grads.append(None)
+                    continue
+                buf = _pinned(batch, ("grad", i), g)
+                buf.copy_(g, non_blocking=True)
+                pinned_grads.append(buf)
+        scal = torch.stack([H.detach(), kl_raw, n_bad])
+        out_pin = _pinned(batch, "scalars", scal)
+        out_pin.copy_(scal, non_blocking=True)
+        if burn is not None:
+            burn.result()
+        torch.cuda.current_stream(dev).synchronize()
+        ent, klv, bad = out_pin[0].clone(), out_pin[1].clone(), out_pin[2].clone()
+        if want_grad:
+            # fresh pageable tensors: the pinned mirrors are reused by the next call on this batch
+            ctx.cpu_grads = [None if g is None else torch.empty(g.shape, dtype=p.dtype).copy_(g)
+                             for g, p in zip(pinned_grads, cpu_params)]
         ctx.mark_non_differentiable(klv, bad)
         return ent, klv, bad
 
     @staticmethod
     def backward(ctx, g_ent, _g1, _g2):
-        grads = torch.autograd.grad(ctx.H, ctx.gp, g_ent.to(ctx.H.device, ctx.H.dtype), allow_unused=True)
-        outs = [None if g is None else g.to("cpu", dt_) for g, dt_ in zip(grads, ctx.dtypes)]
+        scale = g_ent.to(torch.float64)
+        outs = [None if g is None else g * scale.to(g.dtype) for g in ctx.cpu_grads]
         return (None, *outs)
 
 
@@ -310,7 +391,6 @@ def _evaluate(behavioral_policy, target_policy, states, actions, num_traj, real_
               distances, indices, k, G, B, ns, eps):
     batch = _get_batch(states, actions, real_traj_lengths, num_traj)
     handle = _get_handle(distances, indices, k)
-    _burn_rng(batch)
     lb = _behav_logp(behavioral_policy, batch)
     pack = (target_policy, lb, batch, handle, k, ns, G, B, eps)
     return _EntropyBridge.apply(pack, *list(target_policy.parameters()))

@@ -97,3 +97,32 @@ def test_gaussian_log_p_matches_oracle_on_cpu_tensors():
     lp = mepol_b200.gaussian_log_p(p, list(p.parameters()), torch.tensor(s, dtype=torch.float64),
                                    torch.tensor(a, dtype=torch.float64))
     np.testing.assert_allclose(lp.detach().numpy(), g["logp_target"], rtol=1e-12, atol=1e-12)
+
+
+def test_fast_rng_burn_leaves_the_generator_where_the_reference_calls_would():
+    """Q7: the shim advances the global CPU generator exactly like the reference's 2*T randn calls."""
+    import torch
+    from mepol_b200 import entropy as E
+
+    class B:
+        lens = [500, 499, 37, 16, 2]
+        action_dim = 8
+        pinned = {}
+
+    for lens in ([500, 499, 37, 16, 2], [3, 500], [1]):       # the last two contain calls of < 16 elements
+        B.lens = lens
+        B.pinned = {}
+        torch.manual_seed(99)
+        for l in lens:
+            for _ in range(2):
+                torch.randn((l, 8), dtype=torch.float64)
+        want = torch.get_rng_state().clone()
+        torch.manual_seed(99)
+        E._burn_rng(B)
+        assert torch.equal(torch.get_rng_state(), want)
+        torch.manual_seed(99)
+        fut = E._burn_rng_async(B)
+        if fut is not None:
+            fut.result()
+        assert torch.equal(torch.get_rng_state(), want)
+    assert E._burn_fast_ok() in (True, False)
