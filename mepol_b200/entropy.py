@@ -26,13 +26,16 @@ from .knn import _stream_ptr
 POLICY_EPS = 1e-7          # src/utils/dtypes.py:7, used inside get_log_p's variance term only
 _LOG_2PI = math.log(2.0 * math.pi)
 
-_config = {"compute_dtype": torch.float64, "burn_rng": True, "device": None}
+_config = {"compute_dtype": torch.float64, "burn_rng": True, "device": None, "cuda_graphs": True}
 
 
-def configure(compute_dtype=None, burn_rng=None, device=None):
+def configure(compute_dtype=None, burn_rng=None, device=None, cuda_graphs=None):
     """compute_dtype: torch.float64 (default, reproduces the float64 reference to ~1e-12) or
     torch.float32 (the bandwidth-optimal kernels; 1e-5 relative).  burn_rng: consume the same
-    torch.randn draws the reference's get_log_p burns so seeded runs stay aligned."""
+    torch.randn draws the reference's get_log_p burns so seeded runs stay aligned.
+    cuda_graphs: replay the device side of an objective step as one captured CUDA graph per
+    (batch, search result) instead of ~60 separate launches (the step is launch-bound at the
+    reference's batch sizes); same kernels, same results."""
     if compute_dtype is not None:
         if compute_dtype not in (torch.float32, torch.float64):
             raise ValueError("compute_dtype must be torch.float32 or torch.float64")
@@ -41,6 +44,8 @@ def configure(compute_dtype=None, burn_rng=None, device=None):
         _config["burn_rng"] = bool(burn_rng)
     if device is not None:
         _config["device"] = torch.device(device)
+    if cuda_graphs is not None:
+        _config["cuda_graphs"] = bool(cuda_graphs)
 
 
 def _device():
@@ -262,7 +267,6 @@ def _fingerprint(policy):
 
 
 _BURN_FAST = None
-_BURN_POOL = None
 
 
 def _burn_fast_ok():
@@ -304,18 +308,6 @@ def _burn_rng(batch, calls=2):
             torch.randn((l, batch.action_dim), dtype=torch.float64)
 
 
-def _burn_rng_async(batch, calls=2):
-    """The burn runs on a helper thread (torch releases the GIL inside the generator loop) while the
-    caller enqueues the step's device work; nothing else touches the CPU generator meanwhile."""
-    global _BURN_POOL
-    if not _config["burn_rng"]:
-        return None
-    if _BURN_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _BURN_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mepol-burn")
-    return _BURN_POOL.submit(_burn_rng, batch, calls)
-
-
 def _behav_logp(behavioral_policy, batch):
     fp = _fingerprint(behavioral_policy)
     if batch.behav_cache is not None and batch.behav_cache[0] == fp:
@@ -336,52 +328,195 @@ def _pinned(batch, name, like):
     return buf
 
 
+def _device_step(target_policy, dev_params, lb, batch, handle, k, ns, G, B, eps, want_grad):
+    """Forward (+ backward for dH = 1) of the objective on device tensors: (scalars [3], grads|None)."""
+    with torch.set_grad_enabled(want_grad):
+        lt = gaussian_log_p(target_policy, dev_params, batch.states, batch.actions)
+        H, kl_raw, n_bad = iw_entropy(lt, lb, handle, batch.traj_off, batch.n_traj, k, ns, G, B, eps)
+    grads = torch.autograd.grad(H, dev_params, allow_unused=True) if want_grad else None
+    return torch.stack([H.detach(), kl_raw, n_bad]), grads
+
+
+class _StaticHandle:
+    """Search result living in buffers owned by a captured graph (same interface as SearchHandle)."""
+
+    def __init__(self, handle, dt):
+        rowptr, col = handle.csr()
+        self.idx, self.k1, self.n = torch.empty_like(handle.idx), handle.k1, handle.n
+        self._rk, self._csr = torch.empty_like(handle.rk(dt)), (torch.empty_like(rowptr), torch.empty_like(col))
+
+    def load(self, handle, dt):
+        rowptr, col = handle.csr()
+        self.idx.copy_(handle.idx)
+        self._rk.copy_(handle.rk(dt))
+        self._csr[0].copy_(rowptr)
+        self._csr[1].copy_(col)
+
+    def rk(self, dtype):
+        return self._rk
+
+    def csr(self):
+        return self._csr
+
+
+class _StaticBatch:
+    def __init__(self, batch, lb):
+        self.states, self.actions = torch.empty_like(batch.states), torch.empty_like(batch.actions)
+        self.traj_off, self.lb = torch.empty_like(batch.traj_off), torch.empty_like(lb)
+        self.n_traj = batch.n_traj
+
+    def load(self, batch, lb):
+        self.states.copy_(batch.states)
+        self.actions.copy_(batch.actions)
+        self.traj_off.copy_(batch.traj_off)
+        self.lb.copy_(lb)
+
+
+class _StepGraph:
+    """The device side of one objective step as a replayable CUDA graph: pinned parameter mirrors ->
+    device parameters -> MLP -> log-prob -> IW forward (-> IW backward -> MLP backward) -> pinned
+    results.  It is captured ONCE per problem shape: states, actions, behavioural log-probs and the
+    neighbour lists live in buffers the graph owns, and a new epoch's batch / search result is
+    copied into them (a few device-to-device copies) the first time it is seen."""
+
+    def __init__(self, target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad):
+        dev, dt = batch.states.device, batch.states.dtype
+        self.dt = dt
+        self.policy = target_policy
+        self.sb, self.sh = _StaticBatch(batch, lb), _StaticHandle(handle, dt)
+        self.src = None
+        self._load(batch, lb, handle)
+        self.host_params = [torch.empty(p.shape, dtype=dt, pin_memory=True) for p in cpu_params]
+        self.dev_params = [torch.empty(p.shape, dtype=dt, device=dev).requires_grad_(want_grad) for p in cpu_params]
+        self.host_out = torch.empty(3, dtype=torch.float64, pin_memory=True)
+        self.host_grads = [torch.empty(p.shape, dtype=dt, pin_memory=True) for p in cpu_params] if want_grad else None
+        self.want_grad = want_grad
+        for hp, p in zip(self.host_params, cpu_params):
+            hp.copy_(p.detach())
+
+        def body():
+            with torch.no_grad():
+                for hp, dp in zip(self.host_params, self.dev_params):
+                    dp.copy_(hp, non_blocking=True)
+            out, grads = _device_step(target_policy, self.dev_params, self.sb.lb, self.sb, self.sh, k, ns, G, B, eps,
+                                      want_grad)
+            self.host_out.copy_(out, non_blocking=True)
+            self.grad_mask = None if grads is None else [g is not None for g in grads]
+            if grads is not None:
+                for hg, g in zip(self.host_grads, grads):
+                    if g is not None:
+                        hg.copy_(g, non_blocking=True)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up outside capture (cuBLAS handles, allocator)
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def _load(self, batch, lb, handle):
+        # strong references keep the sources alive, so identity is a valid "already loaded" test
+        if self.src is None or self.src[0] is not batch or self.src[1] is not lb:
+            self.sb.load(batch, lb)
+        if self.src is None or self.src[2] is not handle:
+            self.sh.load(handle, self.dt)
+        self.src = (batch, lb, handle)
+
+    def run(self, cpu_params, batch, lb, handle):
+        self._load(batch, lb, handle)
+        for hp, p in zip(self.host_params, cpu_params):
+            hp.copy_(p.detach())
+        self.graph.replay()
+        _burn_rng(batch)                               # host work while the device runs the step
+        torch.cuda.current_stream(batch.states.device).synchronize()
+        out = self.host_out.clone()
+        grads = None
+        if self.want_grad:
+            grads = [torch.empty(p.shape, dtype=p.dtype).copy_(hg) if m else None
+                     for hg, m, p in zip(self.host_grads, self.grad_mask, cpu_params)]
+        return out, grads
+
+
+_graph_failed = False
+_graphs = {}
+
+
+def _step_graph(target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad):
+    """Cached _StepGraph for this problem shape and these objective constants, or None (disabled /
+    a capture failed once: the eager path is used from then on)."""
+    global _graph_failed
+    if not _config["cuda_graphs"] or _graph_failed:
+        return None
+    key = (id(target_policy), str(batch.states.device), batch.states.dtype, tuple(batch.states.shape),
+           tuple(batch.actions.shape), batch.n_traj, handle.n, handle.k1, bool(want_grad), int(k), int(ns), G,
+           float(B), float(eps), tuple(tuple(p.shape) for p in cpu_params))
+    sg = _graphs.get(key)
+    if sg is not None and sg.policy is not target_policy:      # id() reuse after the policy was freed
+        sg = None
+    if sg is None:
+        try:
+            sg = _StepGraph(target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad)
+        except Exception as e:            # capture is an optimisation: never let it break a step
+            _graph_failed = True
+            import warnings
+            warnings.warn(f"mepol_b200: CUDA-graph capture of the objective step failed ({e!r}); using eager launches")
+            torch.cuda.synchronize()
+            return None
+        if len(_graphs) >= 8:
+            _graphs.pop(next(iter(_graphs)))
+        _graphs[key] = sg
+    return sg
+
+
 class _EntropyBridge(torch.autograd.Function):
     """CPU parameters -> (entropy, kl_raw, n_bad) CPU scalars, everything in between on the GPU.
 
     The whole device side of a step -- forward, and when a gradient will be wanted also the backward
-    for dH = 1 plus the device->host copies -- is ENQUEUED first; the Q7 random-number burn (2.5 ms of
-    CPU work at Ant's N = 10000, more than all the GPU work of the step) then runs on the host while
-    the GPU works, and one stream synchronisation ends the call.  backward() only scales the stored
-    gradients by the incoming dH (the loss is -H)."""
+    for dH = 1 plus the device->host copies -- is ENQUEUED first (as one CUDA-graph replay when
+    graphs are enabled); the Q7 random-number burn then runs on the host while the GPU works, and one
+    stream synchronisation ends the call.  backward() only scales the stored gradients by the
+    incoming dH (the loss is -H)."""
 
     @staticmethod
     def forward(ctx, pack, *cpu_params):
-        target_policy, lb, batch, handle, k, ns, G, B, eps = pack
+        target_policy, lb, batch, handle, k, ns, G, B, eps, grad_mode = pack
         dev, dt = batch.states.device, batch.states.dtype
-        want_grad = any(ctx.needs_input_grad[1:])
-        burn = _burn_rng_async(batch)                  # host-side work that overlaps everything below
-        gp = [p.detach().to(device=dev, dtype=dt, non_blocking=True).requires_grad_(want_grad) for p in cpu_params]
-        pinned_grads = None
-        with torch.set_grad_enabled(want_grad):
-            lt = gaussian_log_p(target_policy, gp, batch.states, batch.actions)
-            H, kl_raw, n_bad = iw_entropy(lt, lb, handle, batch.traj_off, batch.n_traj, k, ns, G, B, eps)
-        if want_grad:
-            grads = torch.autograd.grad(H, gp, allow_unused=True)
-            pinned_grads = []
-            for i, (g, p) in enumerate(zip(grads, cpu_params)):
-                if g is None:
-                    pinned_grads.append(None)
-                    continue
-                buf = _pinned(batch, ("grad", i), g)
-                buf.copy_(g, non_blocking=True)
-                pinned_grads.append(buf)
-        scal = torch.stack([H.detach(), kl_raw, n_bad])
-        out_pin = _pinned(batch, "scalars", scal)
-        out_pin.copy_(scal, non_blocking=True)
-        if burn is not None:
-            burn.result()
-        torch.cuda.current_stream(dev).synchronize()
-        ent, klv, bad = out_pin[0].clone(), out_pin[1].clone(), out_pin[2].clone()
-        if want_grad:
-            # fresh pageable tensors: the pinned mirrors are reused by the next call on this batch
-            ctx.cpu_grads = [None if g is None else torch.empty(g.shape, dtype=p.dtype).copy_(g)
-                             for g, p in zip(pinned_grads, cpu_params)]
+        want_grad = grad_mode and any(ctx.needs_input_grad[1:])
+        with torch.cuda.device(dev):
+            sg = _step_graph(target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad)
+            if sg is not None:
+                out, grads = sg.run(cpu_params, batch, lb, handle)
+            else:
+                gp = [p.detach().to(device=dev, dtype=dt).requires_grad_(want_grad) for p in cpu_params]
+                scal, dgrads = _device_step(target_policy, gp, lb, batch, handle, k, ns, G, B, eps, want_grad)
+                out_pin = _pinned(batch, "scalars", scal)
+                out_pin.copy_(scal, non_blocking=True)
+                pins = None
+                if want_grad:
+                    pins = []
+                    for i, g in enumerate(dgrads):
+                        pins.append(None if g is None else _pinned(batch, ("grad", i), g))
+                        if g is not None:
+                            pins[-1].copy_(g, non_blocking=True)
+                _burn_rng(batch)                           # host work while the device runs the step
+                torch.cuda.current_stream(dev).synchronize()
+                out = out_pin.clone()
+                # fresh pageable tensors: the pinned mirrors are reused by the next call on this batch
+                grads = None if pins is None else [None if g is None else torch.empty(g.shape, dtype=p.dtype).copy_(g)
+                                                   for g, p in zip(pins, cpu_params)]
+        ent, klv, bad = out[0].clone(), out[1].clone(), out[2].clone()
+        ctx.cpu_grads = grads
         ctx.mark_non_differentiable(klv, bad)
         return ent, klv, bad
 
     @staticmethod
     def backward(ctx, g_ent, _g1, _g2):
+        if ctx.cpu_grads is None:
+            raise RuntimeError("mepol_b200: entropy was evaluated without gradient tracking")
         scale = g_ent.to(torch.float64)
         outs = [None if g is None else g * scale.to(g.dtype) for g in ctx.cpu_grads]
         return (None, *outs)
@@ -392,7 +527,7 @@ def _evaluate(behavioral_policy, target_policy, states, actions, num_traj, real_
     batch = _get_batch(states, actions, real_traj_lengths, num_traj)
     handle = _get_handle(distances, indices, k)
     lb = _behav_logp(behavioral_policy, batch)
-    pack = (target_policy, lb, batch, handle, k, ns, G, B, eps)
+    pack = (target_policy, lb, batch, handle, k, ns, G, B, eps, torch.is_grad_enabled())
     return _EntropyBridge.apply(pack, *list(target_policy.parameters()))
 
 

@@ -206,3 +206,40 @@ def test_rev_csr_is_the_transpose():
         expect = np.sort(np.nonzero((idx[:, :k] == j).any(1))[0].repeat(1))
         rows = np.repeat(np.arange(n), k)[idx[:, :k].reshape(-1) == j]
         np.testing.assert_array_equal(col[rowptr[j]:rowptr[j + 1]], np.sort(rows))
+
+
+def test_cuda_graph_replay_equals_eager_launches_over_several_steps():
+    """The captured objective step (default) and the eager launches run the same kernels: losses,
+    KLs and parameters after several optimiser steps are bit-identical, and the RNG burn leaves the
+    CPU generator in the same state either way."""
+    from mepol_b200 import entropy as E
+    g = load_golden(golden_files("iw_ragged")[0])
+    T = g["lens"].shape[0]
+    args = (torch.tensor(g["states"], dtype=torch.float64), torch.tensor(g["actions"], dtype=torch.float64), T,
+            torch.tensor(g["lens"], dtype=torch.int64), torch.tensor(g["dist"]), torch.tensor(g["idx"].astype(np.int64)),
+            int(g["k"]), float(g["G"]), float(g["B"]), int(g["ns"]), float(g["eps"]))
+    runs = {}
+    try:
+        for graphs in (True, False):
+            mepol_b200.configure(cuda_graphs=graphs)
+            E._batches.clear()
+            E._handles.clear()
+            E._graphs.clear()
+            beh, tgt = _make_policy(g, "beh"), _make_policy(g, "tgt")
+            opt = torch.optim.Adam(tgt.parameters(), lr=1e-3)
+            torch.manual_seed(7)
+            trace = []
+            for _ in range(4):
+                loss, bad = mepol_b200.policy_update(opt, beh, tgt, *args)
+                with torch.no_grad():
+                    kl, err = mepol_b200.compute_kl(beh, tgt, *args[:7], args[10])
+                trace.append((loss.detach().clone(), kl.clone()))
+            runs[graphs] = (trace, [p.detach().clone() for p in tgt.parameters()], torch.get_rng_state().clone())
+    finally:
+        mepol_b200.configure(cuda_graphs=True)
+    assert not E._graph_failed
+    for (l1, k1), (l2, k2) in zip(runs[True][0], runs[False][0]):
+        assert torch.equal(l1, l2) and torch.equal(k1, k2)
+    for a, b in zip(runs[True][1], runs[False][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(runs[True][2], runs[False][2])

@@ -120,9 +120,42 @@ def test_fast_rng_burn_leaves_the_generator_where_the_reference_calls_would():
         torch.manual_seed(99)
         E._burn_rng(B)
         assert torch.equal(torch.get_rng_state(), want)
-        torch.manual_seed(99)
-        fut = E._burn_rng_async(B)
-        if fut is not None:
-            fut.result()
-        assert torch.equal(torch.get_rng_state(), want)
     assert E._burn_fast_ok() in (True, False)
+
+
+def test_rng_burn_interleaved_with_foreign_draws_and_size_changes():
+    """The shim's burn equals the literal randn calls inside any sequence of other generator uses."""
+    import torch
+    from mepol_b200 import entropy as E
+
+    class B:
+        action_dim = 8
+        pinned = {}
+
+        def __init__(self, lens):
+            self.lens = lens
+            self.pinned = {}
+
+    def literal(lens):
+        for l in lens:
+            for _ in range(2):
+                torch.randn((l, 8), dtype=torch.float64)
+
+    a, b = B([500, 500, 499]), B([37, 64])
+    script = [("burn", a), ("burn", a), ("burn", a), ("draw", None), ("burn", a), ("burn", b), ("burn", a),
+              ("burn", a), ("seed", None), ("burn", a), ("burn", a)]
+    states = {}
+    for mode in ("shim", "literal"):
+        torch.manual_seed(5)
+        trace = []
+        for op, arg in script:
+            if op == "burn":
+                E._burn_rng(arg) if mode == "shim" else literal(arg.lens)
+            elif op == "draw":
+                torch.rand(3)
+            else:
+                torch.manual_seed(11)
+            trace.append(torch.get_rng_state().clone())
+        states[mode] = trace
+    for i, (x, y) in enumerate(zip(states["shim"], states["literal"])):
+        assert torch.equal(x, y), f"generator diverged after script step {i}"
