@@ -40,6 +40,8 @@
 // contiguous, so one 1-D bulk copy per tile lands it in shared memory ready for the descriptor:
 //   byte offset(row r, 16-byte k-chunk c) = ((r/8)*4 + c)*128 + (r%8)*16
 //   descriptor: LBO (next core matrix along K) = 128 B, SBO (next 8-row group) = 512 B.
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 
 namespace mepol {
@@ -80,9 +82,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         const float *__restrict__ q_delta, int n_q, const uint16_t *__restrict__ rb, int n_ref,
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
                         int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
-                        unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode, int n_full_blocks,
+                        unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode_arg, int n_full_blocks,
                         int tail_split, int n_split, int warm_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
+#ifdef MEPOL_BRINGUP
+    const int epi_mode = epi_mode_arg;      // bring-up timing modes (results invalid when non-zero)
+#else
+    constexpr int epi_mode = 0;             // shipped build: the per-tile mode checks fold away
+    (void)epi_mode_arg;
+#endif
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barrier slots.  done0/done1[s]: the MMAs of accumulator 0 / 1 that read B stage s have retired
@@ -354,7 +362,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
             const int rot = kDump ? 0 : (rblk * 2) % tiles;
             const int warm = warm_of(tiles), sweep = tiles + warm;
-            for (int j = 0; j < sweep; ++j, ++it) {
+            // The tile body is instantiated twice (warm-up tiles / sweep proper) so that neither loop
+            // carries the other's per-tile branches on its critical path.
+            auto tile = [&](auto warm_c, int j) {
+                constexpr bool kWarmTile = decltype(warm_c)::value;
                 int jt = j + rot;
                 if (jt >= tiles) jt -= tiles;
                 if (jt >= tiles) jt -= tiles;
@@ -390,14 +401,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 prof[0] += pt1 - pt0;
                 prof[1] += pt2 - pt1;
                 ++prof[5];
-                if (epi_mode == 1 || epi_mode == 2) continue;   // bring-up timing modes: no filter
+                if (epi_mode == 1 || epi_mode == 2) return;   // bring-up timing modes: no filter
                 if (kDump) {
                     if (rblk == 0)
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
 #pragma unroll
                             for (int jj = 0; jj < 32; ++jj) dump[(size_t)rloc * kTcTileRefs + c * 32 + jj] = v[c][jj];
-                    continue;
+                    return;
                 }
                 float gm[4];
 #pragma unroll
@@ -418,18 +429,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                 }
                 const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
-                if (K1 > 0 && j < warm) {
+                if (kWarmTile) {
                     // warm-up tile: the tile minimum is the score of one reference of this tile, so the
                     // k1 smallest minima bound the k1-th smallest score from above (padding references
                     // carry a score above every real one and never are a minimum)
                     topk_insert(mm);
-                    if (live) tau = topk[K1 - 1] + band;
-                    if (j == warm - 1) {
-                        // the sweep proper sees every tile once more: restart the list, keep tau
-#pragma unroll
-                        for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
-                    }
-                    continue;
+                    if (live) tau = topk[K1 > 0 ? K1 - 1 : 0] + band;
+                    return;
                 }
                 const long long pt3 = TC_PROF_NOW();
                 prof[2] += pt3 - pt2;
@@ -475,7 +481,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                     prof[3] += TC_PROF_NOW() - pt3;
                 }
+            };
+            int j = 0;
+            for (; j < warm; ++j, ++it) tile(std::true_type{}, j);
+            if (warm > 0) {
+                // the sweep proper sees every tile once more: restart the list, keep tau
+#pragma unroll
+                for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
             }
+            for (; j < sweep; ++j, ++it) tile(std::false_type{}, j);
             if (!kDump) {
                 // final tightening + coalesced write-out of every row of the warp
                 unsigned need = __ballot_sync(0xffffffffu, live && !ovf && cnt > k1);
