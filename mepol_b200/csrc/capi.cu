@@ -272,7 +272,7 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     if (rc != MEPOL_OK) return rc;
     // rows whose fp16 band overflowed are re-pruned with the fp32 band before the exact fallback
     if (p.algo == MEPOL_KNN_TC && (rc = launch_rescue_simt(p, st)) != MEPOL_OK) return rc;
-#ifdef MEPOL_BRINGUP
+#if defined(MEPOL_BRINGUP) && defined(MEPOL_BRINGUP_MODES)
     {
         const char *em = getenv("MEPOL_TC_EPI_MODE");   // bring-up timing aid: results are invalid, stop here
         if (em && atoi(em) != 0) return MEPOL_OK;

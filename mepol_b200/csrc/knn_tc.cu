@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode_arg, int n_full_blocks,
                         int tail_split, int n_split, int warm_tiles) {
     extern __shared__ __align__(1024) unsigned char smem[];
-#ifdef MEPOL_BRINGUP
+#if defined(MEPOL_BRINGUP) && defined(MEPOL_BRINGUP_MODES)
     const int epi_mode = epi_mode_arg;      // bring-up timing modes (results invalid when non-zero)
 #else
     constexpr int epi_mode = 0;             // shipped build: the per-tile mode checks fold away
@@ -559,7 +559,7 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     const int n_full_blocks = p.tc_tail_split > 1 ? (n_row_blocks / grid) * grid : n_row_blocks;
     const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * p.tc_tail_split;
     if (grid > n_units) grid = n_units;
-#ifdef MEPOL_BRINGUP
+#if defined(MEPOL_BRINGUP) && defined(MEPOL_BRINGUP_MODES)
     const char *em = getenv("MEPOL_TC_EPI_MODE");        // bring-up timing aid (results invalid when set):
     const int epi_mode = em ? atoi(em) : 0;              // 1 = TMEM loads only, 2 = barriers + MMA only
 #else
