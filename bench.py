@@ -374,8 +374,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["tflops"]) if achieved else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-                # (profiles/r01_ncu_tc_v9_raw.txt); only valid for the configuration that capture was taken on
-                "traffic": 1.677e9 if (n == 1048576 and world == 1 and d == 29 and algo != _lib.KNN_SIMT) else None,
+                # (profiles/r01_ncu_tc_v10_raw.txt); only valid for the configuration that capture was taken on
+                "traffic": 1.610e9 if (n == 1048576 and world == 1 and d == 29 and algo != _lib.KNN_SIMT) else None,
                 "kernel": "knn_prune_tc" if (algo != _lib.KNN_SIMT and prune_avg < 400) else "knn_prune",
                 "kernel_ms": prune_avg, "launches_timed": len(prune_ms),
                 "algorithmic_flops_per_launch": flops,
