@@ -413,12 +413,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 float gm[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float m[11];
+                    // 32 -> 1 in 16 instructions (the minimum for 3-input mins): 10 triples + the last two
+                    // raw values make 12, four triples make 4, then one 3-input and one 2-input min
+                    float m[10];
 #pragma unroll
                     for (int g = 0; g < 10; ++g) m[g] = fmin3(v[c][3 * g], v[c][3 * g + 1], v[c][3 * g + 2]);
-                    m[10] = fminf(v[c][30], v[c][31]);
                     const float m0 = fmin3(m[0], m[1], m[2]), m1 = fmin3(m[3], m[4], m[5]);
-                    const float m2 = fmin3(m[6], m[7], m[8]), m3 = fminf(m[9], m[10]);
+                    const float m2 = fmin3(m[6], m[7], m[8]), m3 = fmin3(m[9], v[c][30], v[c][31]);
                     gm[c] = fminf(fmin3(m0, m1, m2), m3);
                     if (c == 1 && !next_ready) {
                         // second probe of the next tile's barrier, anchored inside the min tree: the
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + 1) / kTcStages) & 1, gm[c]);
                     }
                 }
-                const float mm = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+                const float mm = fminf(fmin3(gm[0], gm[1], gm[2]), gm[3]);
                 if (kWarmTile) {
                     // warm-up tile: the tile minimum is the score of one reference of this tile, so the
                     // k1 smallest minima bound the k1-th smallest score from above (padding references
