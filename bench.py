@@ -399,8 +399,9 @@ def run_ours(args):
                           f"{rows} query rows vs all {n} fitted rows ({ts:.1f} s, scaled x{n / rows:.1f}) + float64 numpy "
                           f"port of compute_entropy/compute_kl/backward on all {n} states ({ti:.2f} s)")}
 
-    # search: col mean x2, pack x2, prune, re-rank, fallback list/partial/merge/serial = 11; rev-CSR 6; IW scan, gather, bwd = 3
-    launches_per_step = 11 + 6 + 3
+    # counted in profiles/r01_ncu_launches_bench_v10.csv -- search: column sums + final, pack x2, prune, rescue,
+    # re-rank, fallback list/partial/merge/serial = 11; reverse CSR 6; IW scan, gather, backward elem + reverse scan = 4
+    launches_per_step = 11 + 6 + 4
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "f16",
