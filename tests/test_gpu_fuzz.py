@@ -47,10 +47,45 @@ def test_random_knn_case(seed):
     algos = [_lib.KNN_AUTO, _lib.KNN_SIMT]
     if d <= 29 and k1 <= 12:
         algos.append(_lib.KNN_TC)
+    if d <= 3:
+        algos.append(_lib.KNN_GRID)
     for algo in algos:
         res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), k1, algo=algo)
         assert_knn_matches(res.distances.cpu().numpy(), res.indices.cpu().numpy().astype(np.int64), ref_d, ref_i,
                            x=x, rtol=1e-12, atol_self=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_knn_case_with_separate_queries(seed):
+    """Queries that are not the fitted rows (what a multi-GPU shard or an evaluation batch passes),
+    some of them far outside the fitted set's extent; every path must agree with the oracle and,
+    bit for bit, with each other."""
+    rng = np.random.default_rng(5000 + seed)
+    d = int(rng.choice([1, 2, 3, 4, 6, 7, 16, 24, 29, 40]))
+    k1 = int(rng.choice([1, 5, 5, 12, 30]))
+    n = int(rng.integers(max(k1, 600), 7000))
+    nq = int(rng.integers(1, 900))
+    kind = ["normal", "clusters", "scaled", "lattice"][seed % 4]
+    x = _data(rng, n, d, kind)
+    q = _data(rng, nq, d, kind)
+    if seed % 3 == 0:
+        q[: max(1, nq // 10)] *= 40.0                        # far outside the box / fp16 range of the scaled operands
+    ref_d, ref_i = knn_oracle.knn_c(x, k1, queries=q, mode="kd_tree")
+    algos = [_lib.KNN_AUTO, _lib.KNN_SIMT]
+    if d <= 29 and k1 <= 12:
+        algos.append(_lib.KNN_TC)
+    if d <= 3:
+        algos.append(_lib.KNN_GRID)
+    xt, qt = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda()
+    first = None
+    for algo in algos:
+        res = mepol_b200.knn_device(xt, k1, queries=qt, algo=algo)
+        assert_knn_matches(res.distances.cpu().numpy(), res.indices.cpu().numpy().astype(np.int64), ref_d, ref_i,
+                           x=x, queries=q, rtol=1e-12, atol_self=1e-9)
+        if first is None:
+            first = res
+        else:
+            assert torch.equal(first.indices, res.indices) and torch.equal(first.distances, res.distances)
 
 
 @pytest.mark.parametrize("seed", range(20))
