@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         int n_ref_tiles, int n_row_blocks, const float *__restrict__ glob, int k1,
                         int32_t *__restrict__ cand, int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
                         unsigned long long *__restrict__ stats, float *__restrict__ dump, int epi_mode_arg, int n_full_blocks,
-                        int tail_split, int n_split, int warm_tiles) {
+                        int tail_split, int n_split, int warm_tiles, int k_steps) {
     extern __shared__ __align__(1024) unsigned char smem[];
 #if defined(MEPOL_BRINGUP) && defined(MEPOL_BRINGUP_MODES)
     const int epi_mode = epi_mode_arg;      // bring-up timing modes (results invalid when non-zero)
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const uint64_t bd1 = bd0 + (256 >> 4);
                     const uint32_t d0 = tmem_base + buf * 256 + t * 128;
                     tc_mma_f16(d0, a_desc[0], bd0, kTcIdesc, 0);
-                    tc_mma_f16(d0, a_desc[1], bd1, kTcIdesc, 1);
+                    if (k_steps > 1) tc_mma_f16(d0, a_desc[1], bd1, kTcIdesc, 1);   // d + 3 <= 16 fits one K=16 step
                     tc_commit(my_commit + 8 * st);
 #ifdef MEPOL_BRINGUP
                     const uint32_t ck_issued = (uint32_t)clock64();
@@ -580,7 +580,8 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
 #endif
     kern<<<grid, kTcThreads, smem_bytes, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, n_ref_tiles,
                                                n_row_blocks, p.glob, p.k1, p.cand, p.cand_cnt, p.flag, p.stats, prof_dev,
-                                               epi_mode, n_full_blocks, p.tc_tail_split, p.n_split, warm_tiles);
+                                               epi_mode, n_full_blocks, p.tc_tail_split, p.n_split, warm_tiles,
+                                               p.d + 3 <= 16 ? 1 : 2);
     MEPOL_CUDA_CHECK(cudaGetLastError());
 #ifdef MEPOL_BRINGUP
     if (prof_dev) {
@@ -603,7 +604,7 @@ int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
     auto kern = knn_prune_tc_kernel<true, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
-                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1, 0);
+                                            p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1, 0, p.d + 3 <= 16 ? 1 : 2);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
