@@ -362,6 +362,9 @@ def run_ours(args):
             comp["search_ms"] = t_of(lambda: searcher(shard_dev), 2)
             comp["search_stats"] = {k_: int(v) for k_, v in zip(("candidates", "fallback_rows", "compactions"),
                                                                searcher._out[3].cpu().tolist()[:3])}
+            # the epoch-realistic mix of the reference's off-policy loop -- one search per epoch and
+            # max_off_iters = 30 objective evaluations (forward + backward) on the same particles
+            comp["epoch_mix_states_per_s"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fwd_bwd_ms"]) * 1e-3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
