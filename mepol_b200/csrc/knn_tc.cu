@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // is still loose.  The first `warm` tiles of a unit are therefore only used to bound the k1-th
     // smallest score: the k1 smallest TILE MINIMA (k1 distinct references) are tracked branch-free in
     // registers and nothing is appended; the same tiles are swept again at the end of the unit, now
-    // against a tight tau.  ~3 % more MMA work removes ~70 % of the divergent survivor handling.
-    auto warm_of = [&](int tiles) { return (K1 > 0 && !kDump) ? min(warm_tiles, tiles >> 3) : 0; };
+    // against a tight tau.  ~3 % more MMA work at N = 1M removes two thirds of the compactions; for
+    // short sweeps up to half of the tiles are warmed (measured 2-4 % faster at N = 32k-131k than an
+    // eighth, profiles/r01_tc_pipeline_notes.md).
+    auto warm_of = [&](int tiles) { return (K1 > 0 && !kDump) ? min(warm_tiles, tiles >> 1) : 0; };
     // Register re-distribution at warpgroup granularity (setmaxnreg): the epilogue keeps a whole
     // 128-column row in registers, the producer / issuer / idle warps need almost none.
     // (each role branch issues its own setmaxnreg so that ptxas budgets the branch it sits in)
