@@ -108,3 +108,22 @@ def test_tc_is_scale_invariant(scale):
     assert torch.equal(a.indices, b.indices)
     assert torch.equal(a.distances, b.distances)
     assert b.stats_dict()["tc_overflow_rows"] == 0
+
+
+@pytest.mark.parametrize("n_ref,n_q", [(70000, 50688), (140000, 45568)])   # 2 and 4 reference splits on 148 SMs
+def test_tc_tail_round_reference_splits_match_simt(n_ref, n_q):
+    """Query-row counts whose last persistent-grid round is partial (the multi-GPU shard shape): the
+    tail row blocks are cut into reference-range splits with separate candidate lists that the
+    re-rank merges -- results must not change."""
+    rng = np.random.default_rng(n_q)
+    x = torch.from_numpy(rng.standard_normal((n_ref, 29)).astype(np.float32)).cuda()
+    q = x[:n_q]
+    a = mepol_b200.knn_device(x, 5, queries=q, algo=_lib.KNN_TC)
+    b = mepol_b200.knn_device(x, 5, queries=q, algo=_lib.KNN_SIMT)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+    qq = torch.from_numpy(rng.standard_normal((n_q, 29)).astype(np.float32)).cuda()       # not a slice of the fitted set
+    a = mepol_b200.knn_device(x, 5, queries=qq, algo=_lib.KNN_TC)
+    b = mepol_b200.knn_device(x, 5, queries=qq, algo=_lib.KNN_SIMT)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
