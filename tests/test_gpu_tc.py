@@ -127,3 +127,16 @@ def test_tc_tail_round_reference_splits_match_simt(n_ref, n_q):
     b = mepol_b200.knn_device(x, 5, queries=qq, algo=_lib.KNN_SIMT)
     assert torch.equal(a.indices, b.indices)
     assert torch.equal(a.distances, b.distances)
+
+
+def test_tc_mass_overflow_goes_through_the_fp32_rescue_pass():
+    """Forcing the tensor-core pruner onto 2-D data overflows the fp16 band for almost every row; past
+    16384 flagged rows the SIMT rescue pass re-prunes them in place instead of the per-row exact
+    fallback.  Results stay exact."""
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.uniform(-1, 1, (40000, 2)).astype(np.float32)).cuda()
+    a = mepol_b200.knn_device(x, 5, algo=_lib.KNN_TC)
+    b = mepol_b200.knn_device(x, 5, algo=_lib.KNN_GRID)
+    assert a.stats_dict()["tc_overflow_rows"] > 16384
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
