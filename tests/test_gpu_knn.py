@@ -87,9 +87,10 @@ def test_query_slice_matches_full_search_bitwise():
     assert torch.equal(part.indices, full.indices[100:200])
 
 
-def test_host_entry_points_agree():
+@pytest.mark.parametrize("d", [29, 7, 2])          # tensor-core, tensor-core (one K step), grid
+def test_host_entry_points_agree(d):
     rng = np.random.default_rng(3)
-    x = rng.standard_normal((5000, 29)).astype(np.float32)
+    x = rng.standard_normal((5000, d)).astype(np.float32)
     d1, i1 = mepol_b200.knn(x, 4)
     d2, i2 = mepol_b200.knn_host_c(x, 4)
     assert i1.dtype == np.int64 and d1.dtype == np.float64 and i1.shape == (5000, 5)
