@@ -100,7 +100,7 @@ def test_host_entry_points_agree(d):
     with pytest.raises(ValueError):
         mepol_b200.knn(x[:3], 4)
     bad = x.copy()
-    bad[7, 3] = np.nan
+    bad[7, d - 1] = np.nan
     with pytest.raises(ValueError):
         mepol_b200.knn(bad, 4)
 
