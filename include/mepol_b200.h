@@ -80,6 +80,12 @@ int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const float *q, int64
                           int k1, float *out, void *workspace, size_t workspace_bytes,
                           void *stream);
 
+/* The same hook for the fp16-accumulator pruner (knn_tc2.cu): first 256 query rows against the first
+ * 256 references, out [256, 256] float32 (device). */
+int mepol_debug_tc2_scores(const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d,
+                           int k1, float *out, void *workspace, size_t workspace_bytes,
+                           void *stream);
+
 /* Host-buffer convenience form of the same call (what a ctypes/cgo-style binding of the reference
  * would use): x [n, d] float32 HOST, self-search, outputs HOST int64 / float64 [n, k1] exactly as
  * sklearn returns them.  Allocates, copies H2D, searches, copies D2H, frees, synchronises. */

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mepol_knn_workspace_bytes": (_i32, [_i64, _i64, _i32, _i32, _i32, _c.POINTER(_sz)]),
     "mepol_knn_search_f32": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "mepol_debug_tc_scores": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "mepol_debug_tc2_scores": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "mepol_knn_search_host_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "mepol_rev_csr_workspace_bytes": (_i32, [_i64, _i32, _c.POINTER(_sz)]),
     "mepol_rev_csr": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),

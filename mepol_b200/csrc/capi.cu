@@ -1,5 +1,6 @@
 // C ABI entry points of the k-NN search (include/mepol_b200.h) and the search plan.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "knn_internal.cuh"
@@ -33,6 +34,13 @@ int device_sm_count() {
 }
 
 int mean_blocks_for(int64_t n_ref);
+
+// Experiment switch (read at every launch): which tensor-core pruner serves MEPOL_KNN_TC.
+//   MEPOL_TC_VARIANT = 3 -> knn_tc2.cu (N = 256 MMAs, fp16 accumulators, packed epilogue); else knn_tc.cu
+int tc_variant() {
+    const char *tv = getenv("MEPOL_TC_VARIANT");
+    return tv ? atoi(tv) : 0;
+}
 
 static int simt_dpad(int d) {
     const int opts[] = {4, 8, 16, 24, 32, 48, 64};
@@ -107,7 +115,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rows_per_cta = 256;
         p.n_split = 1;
         p.cap = 32;   // kTcSoftCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
-        p.n_ref_pad = (n_ref + 127) / 128 * 128;
+        p.n_ref_pad = (n_ref + 255) / 256 * 256;   // whole 256-reference B tiles (knn_tc2.cu); knn_tc.cu takes them as 2 x 128
         p.n_q_pad = (n_q + 255) / 256 * 256;
         {
             // Tail balancing of the persistent grid: with few rounds (multi-GPU shards), the blocks of the
@@ -148,6 +156,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rb = c.take<uint16_t>((size_t)p.n_ref_pad * kTcKPad);
         p.qb = c.take<uint16_t>((size_t)p.n_q_pad * kTcKPad);
         p.q_delta = c.take<float>((size_t)n_q);
+        p.q_ahalf = c.take<float>((size_t)n_q);
     }
     if (algo == MEPOL_KNN_GRID) {
         p.grid_pts = c.take<float>((size_t)n_ref * 4);
@@ -265,7 +274,7 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     prof_record(0, st);
     if (p.algo == MEPOL_KNN_TC)
-        rc = launch_prune_tc(p, st);
+        rc = tc_variant() == 3 ? launch_prune_tc2(p, 256, st) : tc_variant() == 4 ? launch_prune_tc2(p, 128, st) : launch_prune_tc(p, st);
     else
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
@@ -301,6 +310,23 @@ extern "C" int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const floa
     if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
     if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     return launch_tc_dump(p, out, st);
+}
+
+// Same hook for knn_tc2.cu: the fp16 accumulator tile of the first 256 query rows against the first
+// 256 references, widened to float, out [256, 256] float (device).
+extern "C" int mepol_debug_tc2_scores(const float *ref, int64_t n_ref, const float *q, int64_t n_q, int d, int k1,
+                                      float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    MEPOL_REQUIRE(ref && q && out && workspace, MEPOL_E_INVALID, "debug_tc2_scores: null pointer");
+    KnnPlan p;
+    int rc = knn_make_plan(p, ref, n_ref, q, n_q, d, k1, MEPOL_KNN_TC, workspace);
+    if (rc != MEPOL_OK) return rc;
+    MEPOL_REQUIRE(workspace_bytes >= p.bytes, MEPOL_E_WORKSPACE, "debug_tc2_scores: workspace %zu < %zu bytes",
+                  workspace_bytes, p.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    return launch_tc2_dump(p, out, st);
 }
 
 __global__ void widen_idx_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {

@@ -20,7 +20,8 @@ __host__ __device__ inline size_t tc_elem_index(int64_t row, int c) {
 }
 
 // indices into the float "glob" array produced by the pack kernels (stored as uint bits, atomicMax)
-enum { G_AMAX = 0, G_DELTA_MAX = 1, G_ATILDE_MAX = 2, G_COUNT = 4 };
+// G_AHALF_MAX: max over the fitted rows of the fp16 operand's norm over its first 16 columns (knn_tc2.cu)
+enum { G_AMAX = 0, G_DELTA_MAX = 1, G_ATILDE_MAX = 2, G_AHALF_MAX = 3, G_COUNT = 4 };
 
 struct KnnPlan {
     int64_t n_q, n_ref;
@@ -44,6 +45,7 @@ struct KnnPlan {
     // tensor-core pruner operands (fp16 stored as uint16), padded to tile multiples
     uint16_t *rb, *qb;
     float *q_delta;
+    float *q_ahalf;    // per query row: norm of the fp16 operand over its first 16 columns (knn_tc2.cu's band)
     int64_t n_ref_pad, n_q_pad;
     // uniform-grid search (d <= 3, knn_grid.cu)
     int grid_g, grid_cells;
@@ -70,6 +72,9 @@ int launch_rescue_simt(const KnnPlan &p, cudaStream_t st);
 bool tc_supported(int d, int k1);
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st);
 int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st);
+// knn_tc2.cu
+int launch_prune_tc2(const KnnPlan &p, int nc, cudaStream_t st);
+int launch_tc2_dump(const KnnPlan &p, float *dump, cudaStream_t st);
 // knn_grid.cu
 bool grid_supported(int d, int k1);
 int grid_cells_per_dim(int64_t n_ref, int d, int k1);

@@ -132,17 +132,17 @@ __global__ void __launch_bounds__(128)
     pack_rows_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int d, int dpad,
                      const double *__restrict__ mean, float *__restrict__ xs, float *__restrict__ nrm,
                      float *__restrict__ anorm, uint16_t *__restrict__ xb, float *__restrict__ delta,
-                     float *__restrict__ glob, int is_ref) {
+                     float *__restrict__ ahalf, float *__restrict__ glob, int is_ref) {
     __shared__ double smean[MEPOL_MAX_DIM];
     if (threadIdx.x < d) smean[threadIdx.x] = mean[threadIdx.x];
     __syncthreads();
     const double sigma = mean[MEPOL_MAX_DIM];
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float a_up = 0.f, delta_up = 0.f, atilde_up = 0.f;
+    float a_up = 0.f, delta_up = 0.f, atilde_up = 0.f, ahalf_up = 0.f;
     if (row < n) {
         const float *xr = x + row * d;
         float *o = xs ? xs + row * dpad : nullptr;
-        double n2 = 0.0, dl2 = 0.0, nt2 = 0.0;
+        double n2 = 0.0, dl2 = 0.0, nt2 = 0.0, nh2 = 0.0;
         bool in_range = true;
         for (int c = 0; c < d; ++c) {
             const double v = ((double)xr[c] - smean[c]) * sigma;   // exact: sigma is a power of two
@@ -164,12 +164,15 @@ __global__ void __launch_bounds__(128)
                 const double hv = (double)__half2float(hb);
                 dl2 += (hv - v) * (hv - v);
                 nt2 += hv * hv;
+                if (c < 16) nh2 += hv * hv;
                 const __half st = is_ref ? __float2half(-2.0f * __half2float(hb)) : hb;   // x2 exact
                 xb[tc_elem_index(row, c)] = __half_as_ushort(st);
             }
             delta_up = in_range ? __double2float_ru(sqrt(dl2) * (1.0 + 1e-12)) : __int_as_float(0x7f800000);
             atilde_up = __double2float_ru(sqrt(nt2) * (1.0 + 1e-12));
+            ahalf_up = __double2float_ru(sqrt(nh2) * (1.0 + 1e-12));
             if (delta) delta[row] = delta_up;
+            if (ahalf) ahalf[row] = ahalf_up;
             if (is_ref) {
                 // ||y'||^2 split over three fp16 columns: hi + mid + lo reproduces it to ~2^-24
                 const __half h = __double2half(n2);
@@ -196,12 +199,13 @@ __global__ void __launch_bounds__(128)
     }
     if (is_ref) {
         // max over the fitted set (bit patterns of non-negative floats order like unsigned ints)
-        float a = warp_max(a_up), dm = warp_max(delta_up), at = warp_max(atilde_up);
+        float a = warp_max(a_up), dm = warp_max(delta_up), at = warp_max(atilde_up), ah = warp_max(ahalf_up);
         if ((threadIdx.x & 31) == 0) {
             atomicMax(reinterpret_cast<unsigned *>(glob + G_AMAX), __float_as_uint(a));
             if (xb) {
                 atomicMax(reinterpret_cast<unsigned *>(glob + G_DELTA_MAX), __float_as_uint(dm));
                 atomicMax(reinterpret_cast<unsigned *>(glob + G_ATILDE_MAX), __float_as_uint(at));
+                atomicMax(reinterpret_cast<unsigned *>(glob + G_AHALF_MAX), __float_as_uint(ah));
             }
         }
     }
@@ -219,7 +223,8 @@ int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref,
     pack_rows_kernel<<<blocks, 128, 0, st>>>(
         x, n, n_pad, d, p.dpad, p.mean, xs, is_ref ? p.r_nrm : nullptr,
         is_ref ? p.r_anorm : p.q_anorm, tc ? (is_ref ? p.rb : p.qb) : nullptr,
-        tc ? (is_ref ? nullptr : p.q_delta) : nullptr, p.glob, is_ref ? 1 : 0);
+        tc ? (is_ref ? nullptr : p.q_delta) : nullptr, tc ? (is_ref ? nullptr : p.q_ahalf) : nullptr, p.glob,
+        is_ref ? 1 : 0);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

@@ -76,7 +76,10 @@ bool tc_supported(int d, int k1) { return d + 3 <= kTcKPad && 2 * k1 + 8 <= kTcS
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ float ld_volatile_f32(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
 
-template <bool kDump, int K1>
+// kVar (experiment switch, MEPOL_TC_VARIANT): 0 = TMEM buffers are handed back to the issuers through
+// mbarriers; 1 = through named hardware barriers (bar.arrive by the 128 epilogue threads of an
+// accumulator, bar.sync by its issuer warp).
+template <bool kDump, int K1, int kVar>
 __global__ void __launch_bounds__(kTcThreads, 1)
     knn_prune_tc_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
                         const float *__restrict__ q_delta, int n_q, const uint16_t *__restrict__ rb, int n_ref,
@@ -92,7 +95,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     (void)epi_mode_arg;
 #endif
     const uint32_t sbase = smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so that per-role addresses
+    // (TMEM, barriers, descriptors) live in uniform registers and tcgen05 operands need no R2UR waterfall
+    const int warp = kVar >= 2 ? __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     // barrier slots.  done0/done1[s]: the MMAs of accumulator 0 / 1 that read B stage s have retired
     // (tcgen05.commit): their accumulator is ready, and once both fired the stage may be refilled.
     const uint32_t bar_full = sbase + kSmemBar;                    // [stages] producer -> issuers
@@ -217,17 +222,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t st = it % kTcStages;
                 const uint32_t buf = it & 1;
                 uint32_t spins = 0;
-                const uint32_t my_bar = (lane == 1) ? bar_full + 8 * st : bar_acc_empty + 8 * (buf * 2 + t);
-                const uint32_t my_par = (lane == 1) ? ((it / kTcStages) & 1) : (((it >> 1) & 1) ^ 1);
-                while (!__all_sync(0xffffffffu, mbar_try_wait(my_bar, my_par))) {
-                    if (++spins > (1u << 25)) __trap();
+                if (kVar == 1) {
+                    // stage first (long complete by the time the buffer comes back), then the hardware
+                    // barrier the accumulator's 128 epilogue threads arrive on after their TMEM load
+                    while (!__all_sync(0xffffffffu, mbar_try_wait(bar_full + 8 * st, (it / kTcStages) & 1))) {
+                        if (++spins > (1u << 25)) __trap();
+                    }
+                    if (it >= 2) named_bar_sync(1 + buf * 2 + t, 160);
+                } else {
+                    const uint32_t my_bar = (lane == 1) ? bar_full + 8 * st : bar_acc_empty + 8 * (buf * 2 + t);
+                    const uint32_t my_par = (lane == 1) ? ((it / kTcStages) & 1) : (((it >> 1) & 1) ^ 1);
+                    while (!__all_sync(0xffffffffu, mbar_try_wait(my_bar, my_par))) {
+                        if (++spins > (1u << 25)) __trap();
+                    }
                 }
                 tc_fence_after();
 #ifdef MEPOL_BRINGUP
                 const uint32_t ck_detect = (uint32_t)clock64();
                 if (t == 1 && lane == 0 && it >= 2) chain[0] += (uint32_t)(ck_detect - ts_s[(it - 2) & 7]);
 #endif
-                if (lane == 0) {
+                if (kVar >= 2 ? elect_one() : lane == 0) {
                     // one K=16 step = two 16-byte k-chunks = 256 bytes further along K
                     const uint64_t bd0 = b_desc0 + (uint64_t)((st * kTcTileBytes) >> 4);
                     const uint64_t bd1 = bd0 + (256 >> 4);
@@ -247,6 +261,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             if (lane == 0) tc_commit(bar_a_empty);   // query tiles reusable once every MMA of the block retired
             __syncwarp();
+        }
+        if (kVar == 1) {
+            // consume the arrivals of the last two tiles so that every barrier ends the kernel idle
+            for (uint32_t i = it >= 2 ? it - 2 : 0; i < it; ++i) named_bar_sync(1 + (i & 1) * 2 + t, 160);
         }
 #ifdef MEPOL_BRINGUP
         if (dump && lane == 0 && !kDump && t == 1) {
@@ -390,8 +408,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
                 if (epi_mode != 2) tc_wait_ld();
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty_addr + 16 * buf);
+                if (kVar == 1) {
+                    named_bar_arrive(1 + buf * 2 + t, 160);
+                } else {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty_addr + 16 * buf);
+                }
                 const long long pt2 = TC_PROF_NOW();
 #ifdef MEPOL_BRINGUP
                 if (warp == 7 && lane == 0) {
@@ -553,7 +575,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     // k+1 = 5 (every shipped MEPOL config but GridWorld) gets the register-resident running top-k1
-    auto kern = p.k1 == 5 ? knn_prune_tc_kernel<false, 5> : knn_prune_tc_kernel<false, 0>;
+    int variant = 0;
+    if (const char *tv = getenv("MEPOL_TC_VARIANT")) variant = atoi(tv);
+    auto kern = p.k1 == 5 ? (variant == 1 ? knn_prune_tc_kernel<false, 5, 1> : variant == 2 ? knn_prune_tc_kernel<false, 5, 2> : knn_prune_tc_kernel<false, 5, 0>)
+                          : (variant == 1 ? knn_prune_tc_kernel<false, 0, 1> : variant == 2 ? knn_prune_tc_kernel<false, 0, 2> : knn_prune_tc_kernel<false, 0, 0>);
     const int smem_bytes = kSmemTotal;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int n_row_blocks = (int)(p.n_q_pad / kTcRows);
@@ -603,7 +628,7 @@ int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
 
 // Test hook: raw accumulator tile (first 256 query rows x first 128 references).
 int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
-    auto kern = knn_prune_tc_kernel<true, 0>;
+    auto kern = knn_prune_tc_kernel<true, 0, 0>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     kern<<<1, kTcThreads, kSmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1, p.glob,
                                             p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 0, 1, 1, 1, 0, p.d + 3 <= 16 ? 1 : 2);
