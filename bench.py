@@ -8,12 +8,19 @@ One "step" = one search of all N synthetic particles (k+1=5, self included), the
 for that search, and one IW-entropy forward (H + KL) + backward on the same N states.
 Prints ONE JSON line on rank 0.
 """
+import os
+import sys
+
+# torchrun exports OMP_NUM_THREADS=1 when it is unset; the reference arm is a CPU measurement "with all
+# the host threads it can use", so undo that BEFORE numpy / sklearn / torch load their OpenMP runtimes.
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1" and (
+        "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ):
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import argparse
 import json
 import math
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -25,7 +32,9 @@ if ROOT not in sys.path:
 
 METRIC = "k-NN entropy states/sec (search + IW fwd/bwd)"
 UNIT = "states/s"
-DIGAMMA = {1: -0.5772156649015329, 4: 1.2561176684318003, 50: 3.9019896734278921}
+# kernels of libmepol_b200.so by name prefix (for the live launch count)
+OUR_KERNEL_PREFIXES = ("knn_", "iw_", "csr_", "pack_rows", "col_sum", "col_mean", "grid_", "rerank", "fallback",
+                       "widen_idx", "merge_", "rescue")
 
 
 def parse_args():
@@ -42,7 +51,13 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the result checks (parity key)")
     return ap.parse_args()
+
+
+def workload_name(n, d, k, traj_len):
+    """ONE string for both arms (the driver compares the two lines' config)."""
+    return f"synthetic sweep N={n} d={d} k={k} L={traj_len} (BASELINE.json configs[4])"
 
 
 def synth(n, d, traj_len, seed=0):
@@ -128,27 +143,39 @@ def measured_peaks():
         return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
 
 
+def traffic_from_capture(kernel, n, d, world):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, but only
+    when that capture was taken on this kernel and this configuration (profiles/*_traffic.json); else null."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if t.get("kernel") == kernel and t.get("n") == n and t.get("d") == d and t.get("n_gpus", 1) == world:
+                return float(t["dram_bytes_per_launch"]), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 # ---------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_once(x, lt, lb, lens, k, n_query_rows, G, B):
-    """Reference CPU path on a bounded sample: sklearn brute/kd-tree search of `n_query_rows` query
-    rows against the full fitted set (cost per query row is independent of how many are asked), and
-    the float64 objective + gradient on all N states.  Returns (t_search_sample, t_iw)."""
-    from oracle import iw_oracle, knn_oracle
-    n = x.shape[0]
-    t0 = time.perf_counter()
-    dist_s, idx_s = knn_oracle.knn_sklearn(x, k + 1, queries=x[:n_query_rows], n_jobs=os.cpu_count())
-    t_search = time.perf_counter() - t0
-    # objective on all N states needs full-size neighbour arrays: tile the sampled rows
-    reps = (n + n_query_rows - 1) // n_query_rows
-    idx = np.tile(idx_s, (reps, 1))[:n]
-    dist = np.tile(dist_s, (reps, 1))[:n]
-    t0 = time.perf_counter()
-    d = x.shape[1]
-    iw_oracle.entropy(lt, lb, lens, dist, idx, k, G, B, d, 0.0)
-    iw_oracle.kl(lt, lb, lens, idx, k, 0.0)
-    iw_oracle.entropy_grad_logp(lt, lb, lens, dist, idx, k, G, d, 0.0)
-    t_iw = time.perf_counter() - t0
-    return t_search, t_iw
+def host_threads():
+    """Use every host core (and say how many the thread pools really have)."""
+    n = os.cpu_count() or 1
+    info = []
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(n)
+        info = [{k: v for k, v in lib.items() if k in ("user_api", "internal_api", "num_threads", "version")}
+                for lib in threadpoolctl.threadpool_info()]
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return n, info
 
 
 def cpu_sample_rows(x, k, target_s):
@@ -165,34 +192,167 @@ def cpu_sample_rows(x, k, target_s):
     return max(256, rows // 256 * 256)
 
 
+class CpuReference:
+    """The reference's CPU implementation of the path on a bounded sample of the workload.
+
+    search   : sklearn's NearestNeighbors exactly as mepol.py:190-192 (fit on all N rows, kneighbors on
+               `rows` of them; the cost per query row of a brute search does not depend on how many rows
+               are asked, so the time is scaled by N / rows and labelled as such);
+    objective: when oracle/_ref is staged (oracle/make_ref.py) the UNMODIFIED reference functions
+               compute_entropy + loss.backward() + compute_kl (mepol.py:142-174, :278) with a float64
+               GaussianPolicy([400, 300], 29, 8) (policy.py:11-61) on `n_obj` states (whole trajectories),
+               scaled by N / n_obj -> kind "reference"; otherwise the numpy port (oracle/iw_oracle.py)
+               on all N states -> kind "port"."""
+
+    def __init__(self, x, lt, lb, lens, k, traj_len, obj_states=131072):
+        self.x, self.lt, self.lb, self.lens, self.k = x, lt, lb, lens, k
+        self.n, self.d = x.shape
+        self.G, self.B = constants(self.d, k)
+        self.kind = "port"
+        self.ref = None
+        try:
+            from oracle import make_ref
+            if make_ref.available():
+                import torch
+                prev = torch.get_default_dtype()
+                self.ref, ref_policy = make_ref.import_reference()     # flips the default dtype (dtypes.py:3)
+                self.torch = torch
+                T = max(1, min(len(lens), obj_states // traj_len))
+                while T > 1 and lens[T - 1] != traj_len:
+                    T -= 1
+                self.T, self.L = T, int(lens[0]) if lens[0] == traj_len else int(lens[0])
+                self.n_obj = int(np.sum(lens[:T]))
+                rng = np.random.default_rng(1)
+                A = 8
+                torch.manual_seed(0)
+                self.behav = ref_policy.GaussianPolicy(num_features=self.d, hidden_sizes=[400, 300], action_dim=A)
+                self.target = ref_policy.GaussianPolicy(num_features=self.d, hidden_sizes=[400, 300], action_dim=A)
+                self.target.load_state_dict(self.behav.state_dict())
+                with torch.no_grad():
+                    for p in self.target.parameters():
+                        p.add_(1e-3 * torch.randn_like(p))
+                self.states = torch.tensor(rng.standard_normal((T, self.L + 1, self.d)), dtype=torch.float64)
+                self.actions = torch.tensor(0.6 * rng.standard_normal((T, self.L, A)), dtype=torch.float64)
+                self.rtl = torch.full((T, 1), self.L, dtype=torch.int64)
+                self.kind = "reference"
+                self._restore = prev
+        except Exception as e:        # the port keeps the arm alive; the line says which one ran
+            self.ref = None
+            self.kind = "port"
+            self.why_port = repr(e)
+
+    def search(self, rows):
+        from oracle import knn_oracle
+        t0 = time.perf_counter()
+        dist_s, idx_s = knn_oracle.knn_sklearn(self.x, self.k + 1, queries=self.x[:rows], n_jobs=os.cpu_count())
+        return time.perf_counter() - t0, dist_s, idx_s
+
+    def objective(self, dist_s, idx_s):
+        """Seconds for one objective evaluation (entropy + backward + KL), scaled to all N states."""
+        rows = idx_s.shape[0]
+        if self.ref is not None:
+            torch = self.torch
+            n_obj = self.n_obj
+            reps = (n_obj + rows - 1) // rows
+            # neighbour lists of the sampled rows tiled over the objective sample (valid indices; the
+            # reference's arithmetic does not depend on which neighbours they are)
+            idx = torch.tensor(np.tile(idx_s % n_obj, (reps, 1))[:n_obj], dtype=torch.int64)
+            dist = torch.tensor(np.tile(dist_s, (reps, 1))[:n_obj], dtype=torch.float64)
+            t0 = time.perf_counter()
+            for p in self.target.parameters():
+                p.grad = None
+            ent = self.ref.compute_entropy(self.behav, self.target, self.states, self.actions, self.T, self.rtl,
+                                           dist, idx, self.k, self.G, self.B, self.d, 0.0)
+            (-ent).backward()
+            with torch.no_grad():
+                self.ref.compute_kl(self.behav, self.target, self.states, self.actions, self.T, self.rtl,
+                                    dist, idx, self.k, 0.0)
+            return (time.perf_counter() - t0) * self.n / n_obj
+        from oracle import iw_oracle
+        reps = (self.n + rows - 1) // rows
+        idx = np.tile(idx_s, (reps, 1))[:self.n]
+        dist = np.tile(dist_s, (reps, 1))[:self.n]
+        lt64, lb64 = self.lt.astype(np.float64), self.lb.astype(np.float64)
+        t0 = time.perf_counter()
+        iw_oracle.entropy(lt64, lb64, self.lens, dist, idx, self.k, self.G, self.B, self.d, 0.0)
+        iw_oracle.kl(lt64, lb64, self.lens, idx, self.k, 0.0)
+        iw_oracle.entropy_grad_logp(lt64, lb64, self.lens, dist, idx, self.k, self.G, self.d, 0.0)
+        return time.perf_counter() - t0
+
+    def describe(self, rows, ts, ti, cores):
+        s = (f"sklearn NearestNeighbors(algorithm=auto, n_jobs={cores}) exactly as mepol.py:190-192: fit on all {self.n} "
+             f"rows, kneighbors on {rows} of them ({ts:.2f} s, scaled x{self.n / rows:.1f}); ")
+        if self.ref is not None:
+            s += (f"unmodified reference compute_entropy + backward + compute_kl (mepol.py:142-174,:278, float64, "
+                  f"GaussianPolicy([400,300],{self.d},8)) from oracle/_ref on {self.n_obj} states "
+                  f"({ti * self.n_obj / self.n:.2f} s, scaled x{self.n / self.n_obj:.1f})")
+        else:
+            s += f"float64 numpy port of compute_entropy/compute_kl/backward on all {self.n} states ({ti:.2f} s)"
+        return s
+
+    def versions(self):
+        import sklearn
+        import scipy
+        import torch
+        return {"sklearn": sklearn.__version__, "torch": torch.__version__, "numpy": np.__version__,
+                "scipy": scipy.__version__}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores, pools = host_threads()
     x, lt, lb, lens = synth(args.n, args.d, args.traj_len)
-    G, B = constants(args.d, args.k)
+    ref = CpuReference(x, lt, lb, lens, args.k, args.traj_len)
     rows = cpu_sample_rows(x, args.k, max(2.0, args.cpu_seconds / 2))
-    times = []
-    for i in range(args.warmup + args.steps):
-        ts, ti = cpu_reference_once(x, lt, lb, lens, args.k, rows, G, B)
-        if i >= args.warmup:
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 3))              # each step is seconds of CPU work; more repeats buy nothing
+    times, ts, ti = [], 0.0, 0.0
+    for i in range(warm + steps):
+        ts, dist_s, idx_s = ref.search(rows)
+        ti = ref.objective(dist_s, idx_s)
+        if i >= warm:
             times.append(ts * args.n / rows + ti)
     per_step = float(np.mean(times))
     value = args.n / per_step
-    sample = (f"sklearn NearestNeighbors (mepol.py:190-192, algorithm=auto, n_jobs={os.cpu_count()}) on {rows} query "
-              f"rows vs all {args.n} fitted rows, scaled x{args.n / rows:.1f}; float64 numpy port of "
-              f"compute_entropy+compute_kl+backward on all {args.n} states")
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"synthetic sweep N={args.n} d={args.d} k={args.k} L={args.traj_len}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(args.n, args.d, args.k, args.traj_len)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
+                             "sample": ref.describe(rows, ts, ti, cores), "threadpools": pools,
+                             "versions": ref.versions(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "steps_requested": args.steps, "warmup_requested": args.warmup}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
+def count_our_launches(fn):
+    """Launches of this repo's kernels in ONE step, counted live with torch.profiler (CUPTI).  Returns
+    (count, {kernel name: launches}) or (None, reason)."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            nm = ev.name
+            if any(p in nm for p in OUR_KERNEL_PREFIXES) and "Memcpy" not in nm and "Memset" not in nm:
+                short = nm.split("<")[0].split("(")[0].replace("void ", "").replace("mepol::", "")
+                names[short] = names.get(short, 0) + 1
+        total = sum(names.values())
+        if total == 0:
+            return None, "profiler saw none of this library's kernels"
+        return total, names
+    except Exception as e:
+        return None, repr(e)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -230,10 +390,12 @@ def run_ours(args):
     lb_dev = lb_pin.to(dev)
     off_dev, _ = mepol_b200.traj_offsets(lens, dev)
     searcher = ShardedSearch(n, d, k1, dev, algo=algo)
-    idx_host = torch.empty((n, k1), dtype=torch.int64).pin_memory() if rank == 0 else None
+    idx_host = torch.empty((n, k1), dtype=torch.int32).pin_memory() if rank == 0 else None
+    idx_host64 = torch.empty((n, k1), dtype=torch.int64) if rank == 0 else None
     dist_host = torch.empty((n, k1), dtype=torch.float64).pin_memory() if rank == 0 else None
     grad_host = torch.empty((n,), dtype=torch.float32).pin_memory() if rank == 0 else None
     scal_host = torch.empty((2,), dtype=torch.float64).pin_memory() if rank == 0 else None
+    copy_stream = torch.cuda.Stream(device=dev)
 
     def objective(idx_full, rk_full, lt_t, lb_t):
         handle = E.SearchHandle(idx_full, rk_full, k1)
@@ -254,18 +416,27 @@ def run_ours(args):
         idx_full, rk_full, dist_full = searcher(sh, gather_distances=True)
         if rank != 0:
             return None
-        idx_host.copy_(idx_full.to(torch.int64), non_blocking=True)             # D2H, sklearn's dtypes
-        dist_host.copy_(dist_full, non_blocking=True)
+        # the neighbour lists go back to the host on a copy stream while the objective runs: int32 over
+        # the bus, widened to sklearn's int64 by the host (half the bytes, no device widening kernel)
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            idx_host.copy_(idx_full, non_blocking=True)                         # D2H indices (int32)
+            dist_host.copy_(dist_full, non_blocking=True)                       # D2H distances (float64)
         ltt = lt_pin.to(dev, non_blocking=True).requires_grad_(True)             # H2D log-probs
         lbt = lb_pin.to(dev, non_blocking=True)
         H, kl_raw, g = objective(idx_full, rk_full, ltt, lbt)
         grad_host.copy_(g, non_blocking=True)                                   # D2H gradient
         scal_host.copy_(torch.stack([H.detach(), kl_raw]), non_blocking=True)   # D2H entropy, KL
+        copy_stream.synchronize()
+        idx_host64.copy_(idx_host)                                              # sklearn's dtype, on the host
         torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream().wait_stream(copy_stream)
         return scal_host
 
     h2d = (hi - lo) * d * 4 + (2 * n * 4 if rank == 0 else 0)
-    d2h = n * k1 * 16 + n * 4 + 16
+    d2h = n * k1 * 12 + n * 4 + 16
 
     def barrier():
         torch.cuda.synchronize()
@@ -289,7 +460,8 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    warmup_done = max(args.warmup, 3)
+    for _ in range(warmup_done):
         step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -310,8 +482,35 @@ def run_ours(args):
         e2e = {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e}
 
+    # ---- per-phase breakdown of one step on this rank, max over ranks (outside the timed region)
+    phases = searcher.timed_phases(shard_dev)
+    if world > 1:
+        keys = sorted(phases)
+        t = torch.tensor([phases[k_] for k_ in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = dict(zip(keys, [float(v) for v in t.tolist()]))
+
+    # ---- result checks (parity key)
+    parity = None
+    if not args.no_verify:
+        idx_full, rk_full, dist_full = searcher(shard_dev, gather_distances=True)
+        if world > 1 and rank == 0:
+            # the same array searched by ONE GPU (rank 0, all rows): the sharded result must be bit-identical
+            full_dev = searcher.full
+            single = mepol_b200.knn_device(full_dev, k1, algo=algo)
+            mism = int((single.indices != idx_full).any(dim=1).sum().item())
+            mism_rk = int((single.rk != rk_full).sum().item())
+            parity = {"vs": "single-GPU search of the same array on rank 0 (bitwise)", "rows_checked": n,
+                      "mismatch": mism, "rk_mismatch": mism_rk}
+            del single
+        elif world == 1:
+            parity = {"vs": None, "rows_checked": 0, "mismatch": None}
+        if world > 1:
+            dist.barrier()
+
     # ---- component timings (outside the timed region; explanatory only)
-    comp = {}
+    comp = {"phases_ms": phases}
+    launches, launch_names = None, None
     if rank == 0:
         def t_of(fn, reps=3):
             torch.cuda.synchronize()
@@ -322,7 +521,7 @@ def run_ours(args):
             b.record()
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
-        idx_full, rk_full, _ = searcher(shard_dev) if world == 1 else (searcher.idx_full, searcher.rk_full, None)
+        idx_full, rk_full = searcher.last_idx, searcher.last_rk
         handle = E.SearchHandle(idx_full, rk_full, k1)
         comp["rev_csr_ms"] = t_of(lambda: E.SearchHandle(idx_full, rk_full, k1).csr())
         handle.csr()
@@ -365,6 +564,15 @@ def run_ours(args):
             # the epoch-realistic mix of the reference's off-policy loop -- one search per epoch and
             # max_off_iters = 30 objective evaluations (forward + backward) on the same particles
             comp["epoch_mix_states_per_s"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fwd_bwd_ms"]) * 1e-3)
+    # live launch count of one step (rank 0 launches the objective as well as its share of the search)
+    if world > 1:
+        dist.barrier()
+    if rank == 0 or world > 1:
+        lc, ln = count_our_launches(step_device)
+        if rank == 0:
+            launches, launch_names = lc, ln
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,15 +582,18 @@ def run_ours(args):
     prune_avg = float(np.mean(prune_ms)) if prune_ms else float("nan")
     flops = 2.0 * (hi - lo) * n * d
     achieved = flops / (prune_avg * 1e-3) / 1e12 if prune_ms else None
+    kernel = _lib.prune_kernel_name(algo, d, k1, n)
+    traffic, traffic_src = traffic_from_capture(kernel, n, d, world)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": (achieved / peaks["tflops"]) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-                # (profiles/r01_ncu_tc_v10_raw.txt); only valid for the configuration that capture was taken on
-                "traffic": 1.610e9 if (n == 1048576 and world == 1 and d == 29 and algo != _lib.KNN_SIMT) else None,
-                "kernel": "knn_prune_tc" if (algo != _lib.KNN_SIMT and prune_avg < 400) else "knn_prune",
-                "kernel_ms": prune_avg, "launches_timed": len(prune_ms),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
+                # of THIS kernel on THIS configuration (null when there is none)
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": kernel, "kernel_ms": prune_avg, "launches_timed": len(prune_ms),
                 "algorithmic_flops_per_launch": flops,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})"}
+                "peak_burst": peaks["tflops_burst"],
+                "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}): the kernel is timed inside a long step"}
     comp["iw_roofline"] = None
     if "iw_kernels_fwd_ms" in comp:
         bytes_iw = (36 + 20 * k) * n
@@ -394,26 +605,37 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        cores, pools = host_threads()
+        ref = CpuReference(x, lt, lb, lens, k, args.traj_len)
         rows = cpu_sample_rows(x, k, args.cpu_seconds)
-        ts, ti = cpu_reference_once(x, lt.astype(np.float64), lb.astype(np.float64), lens, k, rows, G, B)
+        ts, dist_s, idx_s = ref.search(rows)
+        ti = ref.objective(dist_s, idx_s)
+        if getattr(ref, "_restore", None) is not None:
+            torch.set_default_dtype(ref._restore)
         v = n / (ts * n / rows + ti)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": (f"sklearn NearestNeighbors(algorithm=auto, n_jobs={os.cpu_count()}) exactly as mepol.py:190-192 on "
-                          f"{rows} query rows vs all {n} fitted rows ({ts:.1f} s, scaled x{n / rows:.1f}) + float64 numpy "
-                          f"port of compute_entropy/compute_kl/backward on all {n} states ({ti:.2f} s)")}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": ref.describe(rows, ts, ti, cores),
+               "threadpools": pools, "versions": ref.versions()}
+        if not args.no_verify:
+            # the benchmarked array itself: the GPU's rows against sklearn's answer for the sampled rows
+            got_i = searcher.last_idx[:rows].cpu().numpy().astype(np.int64)
+            got_d = searcher.last_dist[:rows].cpu().numpy()
+            bad_rows = int((got_i != idx_s).any(axis=1).sum())
+            far = dist_s > 1e-3                                         # col 0 (self) is ~1e-7 in sklearn's brute form
+            rel = float(np.max(np.abs(got_d[far] - dist_s[far]) / dist_s[far]))
+            parity = {"vs": "sklearn NearestNeighbors on the benchmarked array (the CPU leg's sampled rows)",
+                      "rows_checked": int(rows), "mismatch": bad_rows, "max_rel_dist_err": rel, "dist_rtol": 1e-5}
 
-    # counted in profiles/r01_ncu_launches_bench_v10.csv -- search: column sums + final, pack x2, prune, rescue,
-    # re-rank, fallback list/partial/merge/serial = 11; reverse CSR 6; IW scan, gather, backward elem + reverse scan = 4
-    launches_per_step = 11 + 6 + 4
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": warmup_done, "warmup_requested": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "f16",
             "data": "synthetic",
-            "config": {"workload": f"synthetic sweep N={n} d={d} k={k} L={args.traj_len} (BASELINE.json configs[4])",
+            "config": {"workload": workload_name(n, d, k, args.traj_len),
                        "algo": args.algo, "parallelism": f"query rows sharded x{world}, refs all-gathered (NCCL)",
                        "l2": "inputs larger than L2: packed refs + candidates > 126 MB per step, no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "components": comp}
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": (launches * args.steps) if launches else None,
+            "gpu_launches_per_step": launch_names if launches else {"uncounted": launch_names},
+            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "components": comp}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

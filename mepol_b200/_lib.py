@@ -97,3 +97,20 @@ def profile_read(max_n=64):
     n = _i32(0)
     check(load().mepol_profile_read(buf, max_n, ctypes.byref(n)), "mepol_profile_read")
     return [buf[i] for i in range(n.value)]
+
+
+def prune_kernel_name(algo, d, k1, n_ref):
+    """Name of the kernel mepol_knn_search_f32 spends its time in for this problem (mirrors the AUTO rule
+    of csrc/capi.cu::knn_make_plan and the tensor-core variant switch) -- for bench.py's roofline record."""
+    if algo == KNN_AUTO:
+        if d <= 3:
+            algo = KNN_GRID
+        else:
+            algo = KNN_TC if (d + 3 <= 32 and 2 * k1 + 8 <= 32 and n_ref >= 512 and d >= 4) else KNN_SIMT
+    if algo == KNN_GRID:
+        return "knn_grid_search_kernel"
+    if algo == KNN_SIMT:
+        return "knn_prune_simt_kernel"
+    import os
+    v = os.environ.get("MEPOL_TC_VARIANT", "")
+    return "knn_prune_tc_kernel" if v in ("0", "1", "2") else "knn_prune_tc2_kernel"

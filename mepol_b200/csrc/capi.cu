@@ -35,11 +35,14 @@ int device_sm_count() {
 
 int mean_blocks_for(int64_t n_ref);
 
-// Experiment switch (read at every launch): which tensor-core pruner serves MEPOL_KNN_TC.
-//   MEPOL_TC_VARIANT = 3 -> knn_tc2.cu (N = 256 MMAs, fp16 accumulators, packed epilogue); else knn_tc.cu
+// Which tensor-core pruner serves MEPOL_KNN_TC (read at every launch; an A/B switch for the measurements
+// in profiles/, every variant is exact):
+//   unset / 3 -> knn_tc2.cu, N = 256 MMAs, fp16 accumulators, packed epilogue (the shipped kernel)
+//   4         -> knn_tc2.cu with two 128-column buffers per accumulator
+//   0, 1, 2   -> knn_tc.cu, the fp32-accumulator kernel of round 1 (2 = with warp-uniform tcgen05 operands)
 int tc_variant() {
     const char *tv = getenv("MEPOL_TC_VARIANT");
-    return tv ? atoi(tv) : 0;
+    return tv && *tv ? atoi(tv) : 3;
 }
 
 static int simt_dpad(int d) {
@@ -274,7 +277,10 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
     prof_record(0, st);
     if (p.algo == MEPOL_KNN_TC)
-        rc = tc_variant() == 3 ? launch_prune_tc2(p, 256, st) : tc_variant() == 4 ? launch_prune_tc2(p, 128, st) : launch_prune_tc(p, st);
+        {
+            const int tv = tc_variant();
+            rc = tv == 4 ? launch_prune_tc2(p, 128, st) : (tv >= 0 && tv <= 2) ? launch_prune_tc(p, st) : launch_prune_tc2(p, 256, st);
+        }
     else
         rc = launch_prune_simt(p, st);
     prof_record(1, st);

@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st) {
     // k+1 = 5 (every shipped MEPOL config but GridWorld) gets the register-resident running top-k1
-    int variant = 0;
+    int variant = 2;                                    // MEPOL_TC_VARIANT = 0 / 1 select the round-1 forms (capi.cu::tc_variant)
     if (const char *tv = getenv("MEPOL_TC_VARIANT")) variant = atoi(tv);
     auto kern = p.k1 == 5 ? (variant == 1 ? knn_prune_tc_kernel<false, 5, 1> : variant == 2 ? knn_prune_tc_kernel<false, 5, 2> : knn_prune_tc_kernel<false, 5, 0>)
                           : (variant == 1 ? knn_prune_tc_kernel<false, 0, 1> : variant == 2 ? knn_prune_tc_kernel<false, 0, 2> : knn_prune_tc_kernel<false, 0, 0>);

@@ -44,6 +44,7 @@ class ShardedSearch:
         self.dist_full = None
         self._ws = None
         self._out = None
+        self.last_idx = self.last_rk = self.last_dist = None
 
     def _cuda_search(self, full, queries):
         res = knn_device(full, self.k1, queries=queries, algo=self.algo, workspace=self._ws, out=self._out)
@@ -51,18 +52,61 @@ class ShardedSearch:
         self._out = (res.indices, res.distances, res.rk, res.stats)
         return res.indices, res.distances, res.rk
 
-    def __call__(self, shard, gather_distances=False):
+    def __call__(self, shard, gather_distances=False, _marks=None):
         """shard: float32 [N/G, d] on this rank's device.  Returns (idx_full int32 [N,k1],
         rk_full float64 [N], dist_full or None) -- identical on every rank."""
+        mark = _marks.append if _marks is not None else (lambda _e: None)
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        if _marks is not None:
+            mark(ev())
         if self.world == 1:
+            if _marks is not None:
+                mark(ev())
             idx, dst, rk = self.search_fn(shard, shard)
+            if _marks is not None:
+                mark(ev())
+                mark(ev())
+            self.full = shard
+            self.last_idx, self.last_rk, self.last_dist = idx, rk, dst
             return idx, rk, (dst if gather_distances else None)
         dist.all_gather_into_tensor(self.full, shard.contiguous(), group=self.group)
+        if _marks is not None:
+            mark(ev())
         idx, dst, rk = self.search_fn(self.full, self.full[self.lo:self.hi])
+        if _marks is not None:
+            mark(ev())
         dist.all_gather_into_tensor(self.idx_full, idx.contiguous(), group=self.group)
         dist.all_gather_into_tensor(self.rk_full, rk.contiguous(), group=self.group)
         if gather_distances:
             if self.dist_full is None:
                 self.dist_full = torch.empty((self.n, self.k1), dtype=torch.float64, device=self.device)
             dist.all_gather_into_tensor(self.dist_full, dst.contiguous(), group=self.group)
+        if _marks is not None:
+            mark(ev())
+        self.last_idx, self.last_rk = self.idx_full, self.rk_full
+        self.last_dist = self.dist_full if gather_distances else None
         return self.idx_full, self.rk_full, (self.dist_full if gather_distances else None)
+
+    def timed_phases(self, shard, reps=3):
+        """Per-phase milliseconds of one sharded search on this rank (CUDA events on the launching stream):
+        all-gather of the particles, the search of the own rows (with the pruning kernel's share from the
+        library's own event pair), all-gather of the results."""
+        from . import _lib
+        out = {"gather_particles_ms": 0.0, "search_own_rows_ms": 0.0, "prune_kernel_ms": 0.0, "gather_results_ms": 0.0}
+        self(shard)
+        for _ in range(reps):
+            marks = []
+            _lib.profile_enable(True)
+            self(shard, _marks=marks)
+            torch.cuda.synchronize(self.device)
+            pr = _lib.profile_read(4)
+            _lib.profile_enable(False)
+            out["gather_particles_ms"] += marks[0].elapsed_time(marks[1]) / reps
+            out["search_own_rows_ms"] += marks[1].elapsed_time(marks[2]) / reps
+            out["gather_results_ms"] += marks[2].elapsed_time(marks[3]) / reps
+            out["prune_kernel_ms"] += (pr[0] if pr else 0.0) / reps
+        return out
