@@ -38,7 +38,7 @@ int mean_blocks_for(int64_t n_ref);
 // Which tensor-core pruner serves MEPOL_KNN_TC (read at every launch; an A/B switch for the measurements
 // in profiles/, every variant is exact):
 //   unset / 3 -> knn_tc2.cu, N = 256 MMAs, fp16 accumulators, packed epilogue (the shipped kernel)
-//   4         -> knn_tc2.cu with two 128-column buffers per accumulator
+//   4 / 5     -> knn_tc2.cu with two 128-column buffers per accumulator (5: both unloaded per epilogue iteration)
 //   0, 1, 2   -> knn_tc.cu, the fp32-accumulator kernel of round 1 (2 = with warp-uniform tcgen05 operands)
 int tc_variant() {
     const char *tv = getenv("MEPOL_TC_VARIANT");
@@ -279,7 +279,8 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     if (p.algo == MEPOL_KNN_TC)
         {
             const int tv = tc_variant();
-            rc = tv == 4 ? launch_prune_tc2(p, 128, st) : (tv >= 0 && tv <= 2) ? launch_prune_tc(p, st) : launch_prune_tc2(p, 256, st);
+            rc = tv == 4 ? launch_prune_tc2(p, 128, 1, st) : tv == 5 ? launch_prune_tc2(p, 128, 2, st)
+                 : (tv >= 0 && tv <= 2) ? launch_prune_tc(p, st) : launch_prune_tc2(p, 256, 1, st);
         }
     else
         rc = launch_prune_simt(p, st);

@@ -546,12 +546,21 @@ __global__ void csr_fill_kernel(const int32_t *__restrict__ idx, int n, int k1, 
     const int pos = atomicAdd(cursor + idx[(size_t)i * k1 + m], 1);
     col[pos] = i;
 }
-// per-row insertion sort: atomics filled each row in arbitrary order; sorting makes the backward's
-// summation order (and therefore its bits) reproducible run to run.
-__global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ col) {
+// Per-row sort: atomics filled each row in arbitrary order; sorting makes the backward's summation
+// order (and therefore its bits) reproducible run to run.  The in-degree of a particle is NOT bounded
+// by k: with exact duplicates (MountainCar's wall states) every copy lists the same k lowest-index
+// copies, so a few hub rows collect thousands of entries.  Rows of up to kCsrShortRow entries are
+// insertion-sorted by one thread; longer ones are queued for csr_sort_long_rows_kernel.
+constexpr int kCsrShortRow = 32;
+__global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ col,
+                                     int32_t *__restrict__ long_list, int32_t *__restrict__ long_count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int e0 = rowptr[j], e1 = rowptr[j + 1];
+    if (e1 - e0 > kCsrShortRow) {
+        long_list[atomicAdd(long_count, 1)] = j;   // list order is arbitrary; every row is sorted on its own
+        return;
+    }
     for (int a = e0 + 1; a < e1; ++a) {
         const int v = col[a];
         int b = a - 1;
@@ -560,6 +569,61 @@ __global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, 
             --b;
         }
         col[b + 1] = v;
+    }
+}
+
+// Long rows: one CTA per row, LSD radix sort (4-bit digits) between the row and a scratch copy.  Every
+// thread owns a contiguous slice of the row and a private column of the 16 x 256 histogram, so the
+// scatter is stable without atomics; O(deg * passes / 256) per row whatever the degree.
+constexpr int kCsrLongThreads = 256;
+__global__ void __launch_bounds__(kCsrLongThreads)
+    csr_sort_long_rows_kernel(const int32_t *__restrict__ rowptr, int32_t *__restrict__ col, int32_t *__restrict__ tmp,
+                              const int32_t *__restrict__ long_list, const int32_t *__restrict__ long_count, int passes) {
+    __shared__ int hist[16 * kCsrLongThreads];
+    __shared__ int warp_tot[kCsrLongThreads / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n_long = *long_count;
+    for (int r = blockIdx.x; r < n_long; r += gridDim.x) {
+        const int j = long_list[r];
+        const int e0 = rowptr[j], deg = rowptr[j + 1] - e0;
+        const int per = (deg + kCsrLongThreads - 1) / kCsrLongThreads;
+        const int lo = min(deg, t * per), hi = min(deg, lo + per);
+        int32_t *src = col + e0, *dst = tmp + e0;
+        for (int p = 0; p < passes; ++p) {
+            const int shift = 4 * p;
+#pragma unroll
+            for (int dg = 0; dg < 16; ++dg) hist[dg * kCsrLongThreads + t] = 0;
+            for (int e = lo; e < hi; ++e) ++hist[((src[e] >> shift) & 15) * kCsrLongThreads + t];
+            __syncthreads();
+            // exclusive scan of the 4096 counters in (digit, thread) order: thread t owns entries 16t .. 16t+15
+            int loc[16], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                loc[q] = sum;
+                sum += hist[16 * t + q];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            int base = incl - sum;
+            for (int w = 0; w < warp; ++w) base += warp_tot[w];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) hist[16 * t + q] = base + loc[q];
+            __syncthreads();
+            for (int e = lo; e < hi; ++e) {
+                const int v = src[e];
+                dst[hist[((v >> shift) & 15) * kCsrLongThreads + t]++] = v;
+            }
+            __syncthreads();
+            int32_t *sw = src;
+            src = dst;
+            dst = sw;
+        }
     }
 }
 
@@ -577,6 +641,8 @@ extern "C" int mepol_rev_csr_workspace_bytes(int64_t n, int k, size_t *bytes) {
     c.take<int32_t>((size_t)n + 1);               // deg
     c.take<int32_t>((size_t)n + 1);               // cursor
     c.take<int32_t>((size_t)csr_blocks_for(n) + 1);
+    c.take<int32_t>((size_t)n * k / kCsrShortRow + 2);   // rows queued for the long-row sort (+ their count)
+    c.take<int32_t>((size_t)n * k);                      // scratch copy of col for the long-row sort
     *bytes = c.bytes();
     return MEPOL_OK;
 }
@@ -596,6 +662,10 @@ extern "C" int mepol_rev_csr(const int32_t *idx, int64_t n, int k1, int32_t *row
     const int nb = csr_blocks_for(n);
     int32_t *bsum = c.take<int32_t>((size_t)nb + 1);
     const int k = k1 - 1;
+    int32_t *long_list = c.take<int32_t>((size_t)n * k / kCsrShortRow + 2);
+    int32_t *long_count = long_list + (size_t)n * k / kCsrShortRow + 1;
+    int32_t *tmp = c.take<int32_t>((size_t)n * k);
+    MEPOL_CUDA_CHECK(cudaMemsetAsync(long_count, 0, sizeof(int32_t), st));
     MEPOL_CUDA_CHECK(cudaMemsetAsync(deg, 0, sizeof(int32_t) * ((size_t)n + 1), st));
     const int64_t edges = n * (int64_t)k;
     const int eb = (int)((edges + 255) / 256);
@@ -604,7 +674,16 @@ extern "C" int mepol_rev_csr(const int32_t *idx, int64_t n, int k1, int32_t *row
     csr_scan_sums_kernel<<<1, 32, 0, st>>>(bsum, nb);
     csr_finish_kernel<<<nb, kCsrThreads, 0, st>>>(deg, (int)n, kCsrItems, bsum, rowptr, cursor);
     csr_fill_kernel<<<eb, 256, 0, st>>>(idx, (int)n, k1, cursor, col);
-    csr_sort_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(rowptr, (int)n, col);
+    csr_sort_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(rowptr, (int)n, col, long_list, long_count);
+    {
+        // key = source row index < n; an even number of 4-bit passes leaves the sorted row in col
+        int bits = 1;
+        while ((1LL << bits) < n) ++bits;
+        int passes = (bits + 3) / 4;
+        passes += passes & 1;
+        csr_sort_long_rows_kernel<<<device_sm_count(), kCsrLongThreads, 0, st>>>(rowptr, col, tmp, long_list, long_count,
+                                                                                passes);
+    }
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

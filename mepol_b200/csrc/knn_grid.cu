@@ -253,13 +253,14 @@ __global__ void __launch_bounds__(kGridWarps * 32)
                 }
         }
         // ---- can an unvisited point still enter?  Distance from the query to the nearest face of
-        // the visited block that has cells behind it; a margin of 2e-3 cell edges covers the float32
-        // rounding of the cell assignment (<= g * 3 * 2^-24 < 4e-4 cells for g <= 2048).
+        // the visited block that has cells behind it; the margin covers the float32 rounding of the cell
+        // assignment, which grows with the grid: (x - lo) * inv_h carries ~3 ulp of a value up to g, i.e.
+        // <= g * 3 * 2^-24 cells (4e-4 for g <= 2048, but 0.19 for the 2^20 cells a 1-D grid may have).
         double bound = INF;
         bool covered = true;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-            const double eps = 2e-3 * p.h[c];
+            const double eps = fmax(2e-3, 4.0 * (double)g * 5.9604644775390625e-8) * p.h[c];
             if (cq[c] + r + 1 < g) {
                 covered = false;
                 bound = fmin(bound, p.lo[c] + (double)(cq[c] + r + 1) * p.h[c] - (double)qx[c] - eps);

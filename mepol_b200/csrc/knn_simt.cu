@@ -277,6 +277,17 @@ __global__ void __launch_bounds__(kSimtThreads)
     }
 }
 
+// Rescue or fallback?  The chunk-parallel exact fallback streams every reference k1 times per flagged
+// row (~F * k1 * n_ref * d); one rescue sweep costs about a SIMT pass over the row blocks that hold a
+// flagged row (<= n_q * n_ref * d).  The sweep wins once F * k1 exceeds ~n_q / 8; below that, and always
+// within what the fallback's scratch holds, the flagged rows stay with the fallback.
+static unsigned long long rescue_min_rows(const KnnPlan &p) {
+    long long thr = p.n_q / (8LL * p.k1);
+    if (thr < 64) thr = 64;
+    if (thr > p.fb_max_rows) thr = p.fb_max_rows;
+    return (unsigned long long)thr;
+}
+
 template <int DPAD, int ROWS>
 static int launch_simt_inst(const KnnPlan &p, int n_split, int cap, int rescue, cudaStream_t st) {
     const int R = kSimtThreads * ROWS;
@@ -286,7 +297,7 @@ static int launch_simt_inst(const KnnPlan &p, int n_split, int cap, int rescue, 
     dim3 grid((unsigned)((p.n_q + R - 1) / R), (unsigned)n_split);
     kern<<<grid, kSimtThreads, smem, st>>>(p.qs, p.q_anorm, (int)p.n_q, p.rs, p.r_nrm, (int)p.n_ref, p.glob, p.d,
                                            p.k1, cap, n_split, p.cand, p.cand_cnt, p.flag, rescue,
-                                           (unsigned long long)p.fb_max_rows, rescue ? p.n_split : n_split, p.stats);
+                                           (unsigned long long)rescue_min_rows(p), rescue ? p.n_split : n_split, p.stats);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

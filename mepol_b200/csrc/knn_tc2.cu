@@ -19,14 +19,15 @@
 //     other's second buffer: while the epilogue of one unloads, the tensor pipe fills the other.
 //
 // fp16 accumulation and exactness.  The accumulator is rounded to fp16 after each of the two K = 16
-// steps.  With D1 the value after the first step (|D1| <= 2 ||x~_A|| ||y~_A||, A = the first 16
-// columns) and u = 2^-10 (one fp16 ulp: covers round-to-nearest and truncation alike):
-//     |s~ - s| <= err(s~) = e0 + u (c + |s~|),   c = 2 a~_A(row) max_y ||y~_A||,
-// e0 = the operand-rounding bound of tc_band().  err is monotone, so with t the k1-th smallest score
-// seen, every reference with s~ > tau(t) = t + [2 e0 + 2u (c + |t|)] / (1 - u) has a true score above
-// the true scores of k1 already seen references: dropping it is exact (the argument of DESIGN.md
-// section 2 with a threshold-dependent band).  tests/test_gpu_tc.py checks the raw tile against a
-// float64 emulation and pins the observed rounding (<= 1 ulp per step).
+// steps, and inside a step the 17 addends are aligned to the largest one.  With D1 the value after the
+// first step (|D1| <= c = 2 ||x~_A|| ||y~_A||, A = the first 16 columns), M1, M2 the largest addend of
+// each step, u_r = 2^-10 (one fp16 ulp) and u_i = 2^-12:
+//     |s~ - s| <= err(s~) = e0 + u_r (c + |s~|) + u_i (M1 + M2),
+// e0 = the operand-rounding bound of tc_band().  err is monotone in s~, so with t the k1-th smallest
+// score seen, every reference with s~ > tau(t) = t + [2 e0 + 2 u_r (c + |t|) + 2 u_i (M1 + M2)] / (1 - u_r)
+// has a true score above the true scores of k1 already seen references: dropping it is exact (the
+// argument of DESIGN.md section 2 with a threshold-dependent band).  tests/test_gpu_tc.py checks the raw
+// tile against a float64 emulation and pins the measured constants (half of u_r, u_i).
 //
 // CTA = 256 query rows x a stream of 256-reference B tiles (16 KB, two consecutive operand tiles).
 //   warp 8      bulk-copy producer (cp.async.bulk + mbarrier complete_tx), 3-stage ring
@@ -77,10 +78,13 @@ static_assert(T2Cfg<256>::kStages * T2Cfg<256>::kStageBytes <= 3 * 16384 && T2Cf
 template <int NC> constexpr uint32_t t2_idesc() {
     return (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-constexpr float kT2Ulp = 9.765625e-4f;               // 2^-10: one fp16 ulp, relative
-// rounding error assumed per accumulation step, in ulps.  Measured on B200: round-to-nearest of the exact
-// sum (<= 0.5 ulp, tests/test_gpu_tc.py); the band costs < 1 % per doubling, so 3x that is cheap insurance.
-constexpr float kT2AccUlps = 1.5f;
+// Error model of the tensor core's fp16 accumulation, per K = 16 step (measured on B200 with
+// scripts/exp_tc2.py, pinned by tests/test_gpu_tc.py; each constant is TWICE what was observed, and the
+// band costs < 1 % of the kernel per doubling):
+//   rounding of the accumulator: round-to-nearest, <= 0.5 ulp of the step's result -> assume 1 ulp = 2^-10 |result|
+//   internal alignment of the 17 addends: <= 2^-13 of the step's largest addend   -> assume 2^-12 of it
+constexpr float kT2Ulp = 9.765625e-4f;               // 2^-10
+constexpr float kT2Align = 2.44140625e-4f;           // 2^-12
 
 __device__ __forceinline__ uint32_t hmin2_3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
@@ -125,8 +129,12 @@ __device__ __forceinline__ void tc_ld128_packed(uint32_t taddr, uint32_t (&r)[64
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld_packed(uint32_t taddr, uint32_t (&r)[128]) { tc_ld256_packed(taddr, r); }
-__device__ __forceinline__ void tc_ld_packed(uint32_t taddr, uint32_t (&r)[64]) { tc_ld128_packed(taddr, r); }
+template <int kN> __device__ __forceinline__ void tc_ld_packed_at(uint32_t taddr, uint32_t *r) {
+    if (kN == 128)
+        tc_ld256_packed(taddr, *reinterpret_cast<uint32_t(*)[128]>(r));
+    else
+        tc_ld128_packed(taddr, *reinterpret_cast<uint32_t(*)[64]>(r));
+}
 
 #ifdef MEPOL_BRINGUP
 #define T2_NOW() clock64()
@@ -134,7 +142,10 @@ __device__ __forceinline__ void tc_ld_packed(uint32_t taddr, uint32_t (&r)[64]) 
 #define T2_NOW() 0LL
 #endif
 
-template <bool kDump, int K1, int NC>
+// kFuse = accumulator buffers an epilogue warp unloads per loop iteration (2 only with NC = 128: both
+// 128-column buffers are pulled into 128 registers back to back and filtered as ONE 256-score row, which
+// halves the per-tile fixed costs of the epilogue while the MMAs keep the finer-grained hand-shake)
+template <bool kDump, int K1, int NC, int kFuse>
 __global__ void __launch_bounds__(kT2Threads, 1)
     knn_prune_tc2_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
                          const float *__restrict__ q_delta, const float *__restrict__ q_ahalf, int n_q,
@@ -146,7 +157,9 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = T2Cfg<NC>;
     constexpr int kT2Stages = Cfg::kStages, kT2StageBytes = Cfg::kStageBytes, kT2TileRefs = NC;
-    constexpr int kBufs = Cfg::kBufs, kRegs = Cfg::kRegs, kGroups = Cfg::kGroups;
+    constexpr int kBufs = Cfg::kBufs, kRegs = Cfg::kRegs * kFuse, kGroups = Cfg::kGroups * kFuse;
+    constexpr int kSubRegs = Cfg::kRegs, kSubGroups = Cfg::kGroups;
+    static_assert(kFuse == 1 || (kFuse == 2 && NC == 128), "fusing needs the two-buffer arrangement");
     constexpr uint32_t kT2Idesc = t2_idesc<NC>();
     const uint32_t sbase = smem_u32(smem);
     // the warp index goes through a shuffle: it tells the compiler that it is warp-uniform, so per-role
@@ -161,6 +174,9 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kT2SmemBar + 8 * (3 * kT2Stages + 6));
     volatile uint32_t *ts_s = reinterpret_cast<volatile uint32_t *>(smem + kT2SmemBar + 160);   // bring-up time stamps [16]
 
+#ifdef MEPOL_BRINGUP
+    if (threadIdx.x < 24) ts_s[threadIdx.x] = 0;
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < kT2Stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     // Work units as in knn_tc.cu: whole row blocks, plus the last partial round of the persistent grid
     // cut into reference-range splits with separate candidate lists.
     const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * tail_split;
-    const int tiles_per_split = (n_ref_tiles + tail_split - 1) / tail_split;
+    const int tiles_per_split = ((n_ref_tiles + tail_split - 1) / tail_split + kFuse - 1) / kFuse * kFuse;
     auto unit_of = [&](int u, int &rblk, int &sp, int &tile0) {
         if (u < n_full_blocks) {
             rblk = u;
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         return hi - tile0;
     };
     // warm-up tiles (tau only, swept again at the end of the unit): see knn_tc.cu
-    auto warm_of = [&](int tiles) { return (K1 > 0 && !kDump) ? min(warm_tiles, tiles >> 1) : 0; };
+    auto warm_of = [&](int tiles) { return (K1 > 0 && !kDump) ? (min(warm_tiles, tiles >> 1) & ~(kFuse - 1)) : 0; };
 #define T2_AUX_SETMAXNREG() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kT2AuxRegs))
 
     if (warp == kT2EpiWarps) {
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const uint32_t d_tmem0 = tmem_base + t * 256;
         const uint32_t my_empty0 = bar_acc_empty + 16 * t;
         uint32_t it = 0, rbi = 0;
-        long long iprof[3] = {0, 0, 0};
+        long long iprof[4] = {0, 0, 0, 0};
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
             int rblk, sp, tile0;
             const int tiles = unit_of(u, rblk, sp, tile0);
@@ -267,7 +283,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 tc_fence_after();
                 const long long q1 = T2_NOW();
 #ifdef MEPOL_BRINGUP
-                if (t == 1 && lane == 0 && it >= (uint32_t)kBufs) iprof[2] += (uint32_t)((uint32_t)q1 - ts_s[(it - kBufs) & 7]);
+                if (t == 1 && lane == 0 && it >= (uint32_t)kBufs) {
+                    iprof[2] += (uint32_t)((uint32_t)q1 - ts_s[(it - kBufs) & 7]);
+                    iprof[3] += (uint32_t)((uint32_t)q1 - ts_s[16 + ((it - kBufs) & 7)]);
+                    const_cast<uint32_t *>(ts_s)[16 + ((it - kBufs) & 7)] = 0;
+                }
 #endif
                 if (elect_one()) {
                     const uint64_t bd0 = b_desc_base + (uint64_t)((st * kT2StageBytes) >> 4);
@@ -291,6 +311,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 7 + 3 * t, (unsigned long long)iprof[1]);
             atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 8 + 3 * t, (unsigned long long)it);
             if (t == 1) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 12, (unsigned long long)iprof[2]);
+            if (t == 1) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 14, (unsigned long long)iprof[3]);
         }
 #endif
     } else if (warp < kT2EpiWarps) {
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         float *bufv = reinterpret_cast<float *>(smem + kT2SmemBufV);
         int *bufi = reinterpret_cast<int *>(smem + kT2SmemBufI);
         const int my_base = rloc * kT2BufStride;
-        const float A = glob[G_AMAX], D = glob[G_DELTA_MAX], AhalfMax = glob[G_AHALF_MAX];
+        const float A = glob[G_AMAX], D = glob[G_DELTA_MAX], AhalfMax = glob[G_AHALF_MAX], AtildeMax = glob[G_ATILDE_MAX];
         const float INF = __int_as_float(0x7f800000);
         const uint32_t my_done = t == 0 ? bar_done0 : bar_done1;
         const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
@@ -386,9 +407,16 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             const bool live = row < n_q;
             float tau = live ? INF : -INF;
             // fp16 accumulation: band0 + bandk |t| (c = bound of the accumulator after the first K step)
-            const float c_first = live ? (k_steps > 1 ? 2.0f * q_ahalf[row] * AhalfMax + c_norm_first : 0.f) : 0.f;
-            const float bandk = 2.01f * kT2AccUlps * kT2Ulp * acc_scale;
-            const float band0 = live ? tc_band(q_anorm[row], q_delta[row], A, D) * 1.001f + bandk * c_first + 1e-5f : 0.f;
+            // err(s~) = e0 + u_r (c_first + |s~|) + u_i (M1 + M2):  c_first bounds the accumulator after the first
+            // K step, M1 / M2 the largest addend of each step (a product, the carried accumulator or a norm
+            // column), all by Cauchy-Schwarz on this row's and the fitted set's operand norms
+            const float a_row = live ? q_anorm[row] + q_delta[row] : 0.f;
+            const float c_first = k_steps > 1 ? 2.0f * (live ? q_ahalf[row] : 0.f) * AhalfMax + c_norm_first : 0.f;
+            const float m_add = fmaxf(2.0f * a_row * AtildeMax, 1.001f * A * A);
+            const float bandk = 2.01f * kT2Ulp * acc_scale;
+            const float band0 = live ? tc_band(q_anorm[row], q_delta[row], A, D) * 1.001f + bandk * c_first +
+                                           2.01f * acc_scale * kT2Align * 2.0f * m_add + 1e-5f
+                                     : 0.f;
             uint32_t tau2 = h2_splat_up(tau);
             int cnt = 0;
             bool ovf = false;
@@ -435,32 +463,38 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             };
             auto tile = [&](auto warm_c, int j) {
                 constexpr bool kWarmTile = decltype(warm_c)::value;
-                const uint32_t st = it % kT2Stages;
-                const long long pt0 = T2_NOW();
-                if (!next_ready) mbar_wait(my_done + 8 * st, (it / kT2Stages) & 1);
-                tc_fence_after();
-                const long long pt1 = T2_NOW();
                 uint32_t v[kRegs];
-                const uint32_t buf = kBufs == 2 ? (it & 1) : 0;
-                __syncwarp();
-                tc_ld_packed(tmem_row + buf * NC, v);
-                {   // probe the next tile's barrier while the TMEM load is in flight
-                    const uint32_t st1 = (it + 1) % kT2Stages;
-                    next_ready = mbar_test_wait(my_done + 8 * st1, ((it + 1) / kT2Stages) & 1);
-                }
-                tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty_addr + 8 * buf);
-                long long pt2 = T2_NOW();
+                long long pt2 = 0;
+#pragma unroll
+                for (int sbt = 0; sbt < kFuse; ++sbt) {
+                    const uint32_t its = it + sbt;
+                    const uint32_t st = its % kT2Stages;
+                    const long long pt0 = T2_NOW();
+                    if (!next_ready) mbar_wait(my_done + 8 * st, (its / kT2Stages) & 1);
+                    tc_fence_after();
+                    const long long pt1 = T2_NOW();
+                    const uint32_t buf = kBufs == 2 ? (its & 1) : 0;
+                    __syncwarp();
+                    tc_ld_packed_at<kSubRegs>(tmem_row + buf * NC, v + sbt * kSubRegs);
+                    {   // probe the next buffer's barrier while the TMEM load is in flight
+                        const uint32_t st1 = (its + 1) % kT2Stages;
+                        next_ready = mbar_test_wait(my_done + 8 * st1, ((its + 1) / kT2Stages) & 1);
+                    }
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty_addr + 8 * buf);
+                    pt2 = T2_NOW();
 #ifdef MEPOL_BRINGUP
-                if (warp == 7 && lane == 0) {
-                    ts_s[it & 7] = (uint32_t)pt2;                                   // release of this tile's buffer
-                    chainE += (uint32_t)((uint32_t)pt1 - ts_s[8 + (it & 7)]);       // issued -> seen ready
-                }
+                    if (t == 1 && lane == 0) atomicMax(const_cast<uint32_t *>(ts_s + 16 + (its & 7)), (uint32_t)pt2);   // last release
+                    if (warp == 7 && lane == 0) {
+                        ts_s[its & 7] = (uint32_t)pt2;                                   // release of this tile's buffer
+                        chainE += (uint32_t)((uint32_t)pt1 - ts_s[8 + (its & 7)]);       // issued -> seen ready
+                    }
 #endif
-                prof[0] += pt1 - pt0;
-                prof[1] += pt2 - pt1;
+                    prof[0] += pt1 - pt0;
+                    prof[1] += pt2 - pt1;
+                }
                 ++prof[5];
                 if (has_pending) {
                     drain();
@@ -486,8 +520,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     const uint32_t m4 = hmin2_3(w[12], w[13], w[14]);
                     gm[c] = hmin2_2(hmin2_3(m0, m1, m2), hmin2_3(m3, m4, w[15]));
                     if (c == kGroups / 2 - 1 && !next_ready) {
-                        const uint32_t st1 = (it + 1) % kT2Stages;
-                        next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + 1) / kT2Stages) & 1,
+                        const uint32_t st1 = (it + kFuse) % kT2Stages;
+                        next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + kFuse) / kT2Stages) & 1,
                                                           __uint_as_float(gm[c]));
                     }
                 }
@@ -505,16 +539,19 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 prof[2] += pt3 - pt2;
                 if (__any_sync(0xffffffffu, h2_any_lt(mm2, tau2))) {
                     ++prof[4];
-                    int jt = j + rot;
-                    if (jt >= tiles) jt -= tiles;
-                    if (jt >= tiles) jt -= tiles;
-                    jt += tile0;
-                    // Slow path, first half (needs the tile's registers): per lane and shuffle-free, the bit
-                    // mask of the row's survivors in a 32-score group is built straight from the packed
-                    // registers (bit j = score 2j, bit 16+j = score 2j+1) and the group is parked in the
-                    // lane's private staging row.  tau2 is tau rounded UP to fp16: the mask is a superset,
-                    // the walk compares exactly.  The second half (walk, append, compaction) is DEFERRED
-                    // behind the next tile's TMEM load + release, see drain().
+                    int jts[kFuse];
+#pragma unroll
+                    for (int sbt = 0; sbt < kFuse; ++sbt) {
+                        int jt = j + sbt + rot;
+                        if (jt >= tiles) jt -= tiles;
+                        if (jt >= tiles) jt -= tiles;
+                        jts[sbt] = jt + tile0;
+                    }
+                    // Slow path, first half (the part that needs the tile's registers): for every 32-score group
+                    // in which some row of the warp has a score below its threshold, each lane builds its row's
+                    // survivor mask and parks the group in its private staging row (16 packed registers).
+                    // The walk, append and compaction are DEFERRED behind the next tile's TMEM load + release,
+                    // see drain().
                     unsigned gbits = 0;
 #pragma unroll
                     for (int c = 0; c < kGroups; ++c) gbits |= h2_any_lt(gm[c], tau2) ? (1u << c) : 0u;
@@ -523,7 +560,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     for (int c = 0; c < kGroups; ++c) {
                         if (!(gbits & (1u << c))) continue;
                         if (has_pending) drain();              // a second hit group in one tile (rare)
-                        const int ref0 = jt * kT2TileRefs + c * 32;
+                        const int ref0 = jts[c / kSubGroups] * kT2TileRefs + (c % kSubGroups) * 32;
+                        // bit j = score 2j, bit 16+j = score 2j+1.  tau2 is tau rounded UP to fp16, so the
+                        // mask is a superset of the survivors; the walk compares exactly.  (Building the mask
+                        // from the parked copy inside drain() instead measured 1-3 % slower.)
                         unsigned mask = 0;
                         const __half2 th = *reinterpret_cast<const __half2 *>(&tau2);
 #pragma unroll
@@ -543,13 +583,13 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 }
             };
             int j = 0;
-            for (; j < warm; ++j, ++it) tile(std::true_type{}, j);
+            for (; j < warm; j += kFuse, it += kFuse) tile(std::true_type{}, j);
             if (warm > 0) {
 #pragma unroll
                 for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
                 tau2 = h2_splat_up(tau);
             }
-            for (; j < sweep; ++j, ++it) tile(std::false_type{}, j);
+            for (; j < sweep; j += kFuse, it += kFuse) tile(std::false_type{}, j);
             if (has_pending) drain();
             if (!kDump) {
                 unsigned need = __ballot_sync(0xffffffffu, live && !ovf && cnt > k1);
@@ -610,9 +650,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 // a single step and no intermediate rounding)
 static float t2_c_norm_first(int d) { return (d < 16 && d + 3 > 16) ? 1.0f : 0.f; }
 
-int launch_prune_tc2(const KnnPlan &p, int nc, cudaStream_t st) {
-    auto kern = nc == 256 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 256> : knn_prune_tc2_kernel<false, 0, 256>)
-                          : (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128> : knn_prune_tc2_kernel<false, 0, 128>);
+int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st) {
+    auto kern = nc == 256 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 256, 1> : knn_prune_tc2_kernel<false, 0, 256, 1>)
+                : fuse == 2 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 2> : knn_prune_tc2_kernel<false, 0, 128, 2>)
+                            : (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 1> : knn_prune_tc2_kernel<false, 0, 128, 1>);
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemTotal));
     const int n_row_blocks = (int)(p.n_q_pad / kT2Rows);
     const int n_ref_tiles = (int)(p.n_ref_pad / nc);
@@ -620,7 +661,9 @@ int launch_prune_tc2(const KnnPlan &p, int nc, cudaStream_t st) {
     const int n_full_blocks = p.tc_tail_split > 1 ? (n_row_blocks / grid) * grid : n_row_blocks;
     const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * p.tc_tail_split;
     if (grid > n_units) grid = n_units;
-    int warm_tiles = 256 * 128 / nc;
+    // Warm-up tiles pay for themselves only on short sweeps (measured, profiles/r02_tc2_notes.md: -5..-8 % at
+    // N = 64k-131k, neutral at 512k, +3 % at 1M where the deferred survivor path is cheap enough on its own)
+    int warm_tiles = p.n_ref_pad >= 786432 ? 0 : 256 * 128 / nc;
     if (const char *wt = getenv("MEPOL_TC_WARM_TILES")) warm_tiles = atoi(wt) * 128 / nc;   // tuning aid; any value >= 0 is exact
     if (warm_tiles < 0) warm_tiles = 0;
     float acc_scale = 1.0f;   // experiment knob: scales the fp16-accumulation part of the band (exact only for >= 1)
@@ -654,8 +697,8 @@ int launch_prune_tc2(const KnnPlan &p, int nc, cudaStream_t st) {
                 fprintf(stderr, "[tc2 prof] issuer %d: cycles/tile: wait (stage + accumulator) %.1f  fence+issue %.1f\n", t,
                         (double)h[6 + 3 * t] / h[8 + 3 * t], (double)h[7 + 3 * t] / h[8 + 3 * t]);
         if (h[11])
-            fprintf(stderr, "[tc2 chain] accumulator 1, cycles/tile: release (warp 7) -> issuer detects %.1f   issued -> epilogue (warp 7) sees ready %.1f\n",
-                    (double)h[12] / h[11], (double)h[13] / h[11]);
+            fprintf(stderr, "[tc2 chain] accumulator 1, cycles/tile: release (warp 7) -> issuer detects %.1f   LAST release -> issuer detects %.1f   issued -> epilogue (warp 7) sees ready %.1f\n",
+                    (double)h[12] / h[11], (double)h[14] / h[11], (double)h[13] / h[11]);
     }
 #endif
     return MEPOL_OK;
@@ -663,7 +706,7 @@ int launch_prune_tc2(const KnnPlan &p, int nc, cudaStream_t st) {
 
 // Test hook: raw fp16 accumulator tile (first 256 query rows x first 256 references) as float.
 int launch_tc2_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
-    auto kern = knn_prune_tc2_kernel<true, 0, 256>;
+    auto kern = knn_prune_tc2_kernel<true, 0, 256, 1>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemTotal));
     kern<<<1, kT2Threads, kT2SmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, p.q_ahalf, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1,
                                               p.glob, p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 1, 1, 1, 0,

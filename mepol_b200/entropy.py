@@ -224,16 +224,25 @@ _batches = {}
 _handles = {}
 
 
+_CACHE_CAP = 8
+
+
+def _cache_prune(table, room_for=1):
+    """Drop entries whose key object died, then the oldest ones, so that `room_for` more fit under the
+    cap.  Entries hold device memory (indices, reverse CSR, workspaces): the tables must stay bounded
+    even when every lookup is a hit on the newest entry (the drop-in attaches one handle per epoch)."""
+    for k_ in [k_ for k_, v in table.items() if v[0]() is None]:
+        del table[k_]
+    while len(table) > _CACHE_CAP - room_for:
+        table.pop(next(iter(table)))
+
+
 def _cache_get(table, key_obj, extra, build):
     key = (id(key_obj), extra)
     hit = table.get(key)
     if hit is not None and hit[0]() is key_obj:
         return hit[1]
-    if len(table) > 8:
-        for k_ in [k_ for k_, v in table.items() if v[0]() is None]:
-            del table[k_]
-        while len(table) > 8:
-            table.pop(next(iter(table)))
+    _cache_prune(table)
     val = build()
     table[key] = (weakref.ref(key_obj), val)
     return val
@@ -248,6 +257,7 @@ def _get_batch(states, actions, real_traj_lengths, num_traj):
 def attach_handle(indices_cpu, handle):
     """Remember the device-side search result that produced a CPU `indices` tensor (so the objective
     does not have to re-upload it)."""
+    _cache_prune(_handles)
     _handles[(id(indices_cpu), handle.k1)] = (weakref.ref(indices_cpu), handle)
 
 
@@ -340,17 +350,21 @@ def _device_step(target_policy, dev_params, lb, batch, handle, k, ns, G, B, eps,
 class _StaticHandle:
     """Search result living in buffers owned by a captured graph (same interface as SearchHandle)."""
 
-    def __init__(self, handle, dt):
-        rowptr, col = handle.csr()
+    def __init__(self, handle, dt, want_grad):
         self.idx, self.k1, self.n = torch.empty_like(handle.idx), handle.k1, handle.n
-        self._rk, self._csr = torch.empty_like(handle.rk(dt)), (torch.empty_like(rowptr), torch.empty_like(col))
+        self._rk = torch.empty_like(handle.rk(dt))
+        self._csr = None
+        if want_grad:          # the reverse CSR only serves the backward: KL / no_grad graphs never build it
+            rowptr, col = handle.csr()
+            self._csr = (torch.empty_like(rowptr), torch.empty_like(col))
 
     def load(self, handle, dt):
-        rowptr, col = handle.csr()
         self.idx.copy_(handle.idx)
         self._rk.copy_(handle.rk(dt))
-        self._csr[0].copy_(rowptr)
-        self._csr[1].copy_(col)
+        if self._csr is not None:
+            rowptr, col = handle.csr()
+            self._csr[0].copy_(rowptr)
+            self._csr[1].copy_(col)
 
     def rk(self, dtype):
         return self._rk
@@ -383,7 +397,7 @@ class _StepGraph:
         dev, dt = batch.states.device, batch.states.dtype
         self.dt = dt
         self.policy = target_policy
-        self.sb, self.sh = _StaticBatch(batch, lb), _StaticHandle(handle, dt)
+        self.sb, self.sh = _StaticBatch(batch, lb), _StaticHandle(handle, dt, want_grad)
         self.src = None
         self._load(batch, lb, handle)
         self.host_params = [torch.empty(p.shape, dtype=dt, pin_memory=True) for p in cpu_params]
@@ -441,34 +455,48 @@ class _StepGraph:
         return out, grads
 
 
-_graph_failed = False
+_graph_failures = 0          # capture is an optimisation: after a few failures stop trying (per process)
+_graph_bad_keys = set()
+_graph_seen = {}             # key -> sightings: a shape is captured the SECOND time it shows up
 _graphs = {}
 
 
 def _step_graph(target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad):
     """Cached _StepGraph for this problem shape and these objective constants, or None (disabled /
     a capture failed once: the eager path is used from then on)."""
-    global _graph_failed
-    if not _config["cuda_graphs"] or _graph_failed:
+    global _graph_failures
+    if not _config["cuda_graphs"] or _graph_failures >= 3:
         return None
     key = (id(target_policy), str(batch.states.device), batch.states.dtype, tuple(batch.states.shape),
            tuple(batch.actions.shape), batch.n_traj, handle.n, handle.k1, bool(want_grad), int(k), int(ns), G,
            float(B), float(eps), tuple(tuple(p.shape) for p in cpu_params))
-    sg = _graphs.get(key)
+    if key in _graph_bad_keys:
+        return None
+    sg = _graphs.pop(key, None)
     if sg is not None and sg.policy is not target_policy:      # id() reuse after the policy was freed
         sg = None
     if sg is None:
+        # A capture costs two warm-up runs plus the capture itself.  Shapes that show up once (the
+        # full-entropy evaluation, every epoch of an environment with early termination) run eagerly;
+        # a shape is captured the second time it is seen.
+        seen = _graph_seen.get(key, 0) + 1
+        if len(_graph_seen) > 64:
+            _graph_seen.clear()
+        _graph_seen[key] = seen
+        if seen < 2:
+            return None
         try:
             sg = _StepGraph(target_policy, cpu_params, lb, batch, handle, k, ns, G, B, eps, want_grad)
-        except Exception as e:            # capture is an optimisation: never let it break a step
-            _graph_failed = True
+        except Exception as e:            # never let a failed capture break a step
+            _graph_failures += 1
+            _graph_bad_keys.add(key)
             import warnings
             warnings.warn(f"mepol_b200: CUDA-graph capture of the objective step failed ({e!r}); using eager launches")
             torch.cuda.synchronize()
             return None
-        if len(_graphs) >= 8:
+        while len(_graphs) >= 8:
             _graphs.pop(next(iter(_graphs)))
-        _graphs[key] = sg
+    _graphs[key] = sg              # (re-)inserted last: eviction is least-recently-used
     return sg
 
 

@@ -19,10 +19,18 @@ for n in sizes:
     rng = np.random.default_rng(0)
     x = torch.from_numpy(rng.standard_normal((n, d), dtype=np.float32)).cuda()
     base = None
+    extra_set = []
     for v in variants:
-        # "3@0.5" = variant 3 with MEPOL_TC2_ACC_SCALE=0.5
-        os.environ["MEPOL_TC_VARIANT"] = v.split("@")[0]
-        os.environ["MEPOL_TC2_ACC_SCALE"] = v.split("@")[1] if "@" in v else "1" 
+        # "3;MEPOL_TC_WARM_TILES=64;X=Y" = variant 3 with extra environment settings for this run
+        parts = v.split(";")
+        os.environ["MEPOL_TC_VARIANT"] = parts[0]
+        for kv in extra_set:
+            os.environ.pop(kv, None)
+        extra_set = []
+        for kv in parts[1:]:
+            key, val = kv.split("=")
+            os.environ[key] = val
+            extra_set.append(key)
         r = mepol_b200.knn_device(x, k1, algo=_lib.KNN_TC)
         torch.cuda.synchronize()
         reps = 5 if n <= 1048576 else 2

@@ -96,3 +96,26 @@ def test_grid_non_finite_rows_fall_back():
     ref = mepol_b200.knn_device(x, 5, queries=q, algo=_lib.KNN_SIMT)
     assert torch.equal(res.indices[ok], ref.indices[ok])
     assert res.stats_dict()["fallback_rows"] >= 1
+
+
+@pytest.mark.parametrize("kind", ["uniform", "gauss"])
+def test_one_dimensional_grid_with_a_huge_cell_count_stays_exact(kind):
+    """d = 1 lets the grid grow to 2^20 cells, where the float32 cell assignment is off by up to ~0.2
+    cells: the stop test's margin must scale with the grid.  Checked against the C oracle on
+    sampled rows and against the SIMT pruner on a query slice."""
+    from oracle import knn_oracle
+    rng = np.random.default_rng(31)
+    n = 300000
+    x = (rng.uniform(-1000, 1000, (n, 1)) if kind == "uniform" else rng.standard_normal((n, 1)) * 50).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    res = mepol_b200.knn_device(xt, 5, algo=_lib.KNN_GRID)
+    rows = np.sort(rng.choice(n, 2000, replace=False))
+    ref_d, ref_i = knn_oracle.knn_c(x, 5, queries=x[rows], mode="kd_tree")
+    got_i = res.indices[torch.from_numpy(rows).cuda()].cpu().numpy()
+    got_d = res.distances[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert_knn_matches(got_d, got_i, ref_d, ref_i, x, queries=x[rows], rtol=1e-12)
+    q = xt[100000:116384]
+    a = mepol_b200.knn_device(xt, 5, queries=q, algo=_lib.KNN_SIMT)
+    b = mepol_b200.knn_device(xt, 5, queries=q, algo=_lib.KNN_GRID)
+    assert torch.equal(a.distances, b.distances)
+    assert torch.equal(a.indices, b.indices)

@@ -140,3 +140,120 @@ def test_tc_mass_overflow_goes_through_the_fp32_rescue_pass():
     assert a.stats_dict()["tc_overflow_rows"] > 16384
     assert torch.equal(a.indices, b.indices)
     assert torch.equal(a.distances, b.distances)
+
+
+# ------------------------------------------------------------------------------------------------
+# Second-generation pruner (knn_tc2.cu): N = 256 MMAs with fp16 accumulators.  The band the kernel
+# prunes with assumes at most one fp16 ulp of error per accumulation step;
+# the raw tile pins what the hardware really does.
+# ------------------------------------------------------------------------------------------------
+def _ulp16(v):
+    a = np.maximum(np.abs(v), 2.0 ** -14)
+    return 2.0 ** (np.floor(np.log2(a)) - 10)
+
+
+def _tc2_operands(x):
+    """knn_prep.cu's packing in float64 with correctly rounded fp16 conversions (numpy rounds
+    float64 -> float16 directly; torch goes through float32 and double-rounds near ties)."""
+    xd = x.astype(np.float64)
+    mean = (xd.sum(0) / x.shape[0]).astype(np.float32).astype(np.float64)
+    ext = np.maximum(xd.max(0) - mean, mean - xd.min(0))
+    sigma = 2.0 ** np.floor(np.log2(128.0 / np.sqrt((ext ** 2).sum())))
+    xc = (xd - mean) * sigma
+    xb = xc.astype(np.float16).astype(np.float64)
+    n2 = (xc * xc).sum(1)
+    h = n2.astype(np.float16).astype(np.float64)
+    m = (n2 - h).astype(np.float16).astype(np.float64)
+    l = (n2 - h - m).astype(np.float16).astype(np.float64)
+    return xb, [h, m, l]
+
+
+@pytest.mark.parametrize("d,kind", [(29, "normal"), (29, "traj"), (29, "offset"), (24, "normal"), (16, "normal"),
+                                    (14, "normal"), (13, "normal"), (7, "normal")])
+def test_tc2_fp16_accumulator_tile_and_rounding_model(d, kind):
+    rng = np.random.default_rng(100 + d)
+    n = 2048
+    x = rng.standard_normal((n, d))
+    if kind == "traj":
+        x = np.cumsum(0.05 * x, axis=0)
+    if kind == "offset":
+        x = x + 100.0
+    x = x.astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    out = torch.full((256, 256), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(_lib.knn_workspace_bytes(n, n, d, 5, _lib.KNN_TC), dtype=torch.uint8, device="cuda")
+    rc = _lib.load().mepol_debug_tc2_scores(xt.data_ptr(), n, xt.data_ptr(), n, d, 5, out.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mepol_debug_tc2_scores")
+    got = out.cpu().numpy().astype(np.float64)
+    assert not np.isnan(got).any()
+    xb, nrm = _tc2_operands(x)
+    q, r = xb[:256], xb[:256]
+    # operand columns: d coordinates, then n_hi, n_mid, n_lo; the first K = 16 step covers columns 0..15
+    cols_q = np.concatenate([q, np.ones((256, 3))], axis=1)
+    cols_r = np.concatenate([-2.0 * r, np.stack([nv[:256] for nv in nrm], axis=1)], axis=1)
+    exact = cols_q @ cols_r.T
+    two_steps = d + 3 > 16
+    d1 = cols_q[:, :16] @ cols_r[:, :16].T if two_steps else np.zeros_like(exact)
+    err = np.abs(got - exact)
+    # measured on B200: round-to-nearest of the exact sum after each step (<= 0.5 ulp each); the kernel's
+    # band assumes kT2AccUlps = 1.5 ulp per step.  Anything above 0.75 would mean the model needs revisiting.
+    bound = (_ulp16(d1) if two_steps else 0.0) + _ulp16(exact)
+    assert np.max(err / bound) <= 0.75, float(np.max(err / bound))
+
+
+@pytest.mark.parametrize("variant", ["0", "2", "3", "4", "5"])
+def test_every_tensor_core_variant_is_bit_identical_to_simt(variant, monkeypatch):
+    """MEPOL_TC_VARIANT is an A/B switch between exact kernels (csrc/capi.cu::tc_variant)."""
+    rng = np.random.default_rng(77)
+    x = torch.from_numpy(rng.standard_normal((70000, 29)).astype(np.float32)).cuda()
+    a = mepol_b200.knn_device(x, 5, algo=_lib.KNN_SIMT)
+    monkeypatch.setenv("MEPOL_TC_VARIANT", variant)
+    b = mepol_b200.knn_device(x, 5, algo=_lib.KNN_TC)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+    q = x[:45568]                                    # partial last round -> reference-range splits
+    a = mepol_b200.knn_device(x, 5, queries=q, algo=_lib.KNN_SIMT)
+    b = mepol_b200.knn_device(x, 5, queries=q, algo=_lib.KNN_TC)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+
+
+def _adversarial(kind, rng):
+    n, d = 30000, 29
+    x = rng.standard_normal((n, d))
+    if kind == "huge_column":          # one coordinate dominates every norm: massive cancellation in the scores
+        x[:, 0] *= 1000.0
+    elif kind == "scaling_edge":       # an outlier that lands exactly on the fp16 scaling limit (norm 128 after scaling)
+        x[0] = 0.0
+        x[0, 3] = np.abs(x).max() * 7.0
+    elif kind == "outliers":           # a few far points with huge ||y||^2 next to a dense core
+        x[:50] *= 12.0
+    elif kind == "tight_trajectories":  # neighbour gaps far below the row norms
+        x = np.cumsum(0.01 * x.reshape(60, 500, d), axis=1).reshape(n, d) + rng.standard_normal((60, 1, d)).repeat(500, 1).reshape(n, d) * 3
+    elif kind == "first_half_heavy":   # all the energy in the first 16 coordinates (the first K step)
+        x[:, 16:] *= 1e-3
+    elif kind == "second_half_heavy":
+        x[:, :16] *= 1e-3
+    elif kind == "lattice":            # masses of exact ties
+        x = rng.integers(-3, 4, (n, d)).astype(np.float64)
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["huge_column", "scaling_edge", "outliers", "tight_trajectories", "first_half_heavy",
+                                  "second_half_heavy", "lattice"])
+@pytest.mark.parametrize("variant", ["3", "2"])
+def test_band_holds_on_adversarial_data(kind, variant, monkeypatch):
+    """The pruning band is a proof obligation, not an observation: on data built to stress it (fp16
+    scaling edge, one huge column, outliers, cancellation inside one K step, exact ties) the tensor-core
+    result must still equal the fp32 SIMT pruner's bit for bit (both are exact)."""
+    x = torch.from_numpy(_adversarial(kind, np.random.default_rng(5))).cuda()
+    a = mepol_b200.knn_device(x, 5, algo=_lib.KNN_SIMT)
+    monkeypatch.setenv("MEPOL_TC_VARIANT", variant)
+    b = mepol_b200.knn_device(x, 5, algo=_lib.KNN_TC)
+    assert torch.equal(a.distances, b.distances)
+    if kind == "lattice":
+        # exact ties: indices are decided by (d^2, index) in both paths
+        assert torch.equal(a.indices, b.indices)
+    else:
+        assert torch.equal(a.indices, b.indices)

@@ -159,3 +159,27 @@ def test_rng_burn_interleaved_with_foreign_draws_and_size_changes():
         states[mode] = trace
     for i, (x, y) in enumerate(zip(states["shim"], states["literal"])):
         assert torch.equal(x, y), f"generator diverged after script step {i}"
+
+
+def test_attached_handles_stay_bounded():
+    """dropin.search_particles attaches one device handle per epoch; every later lookup hits the newest
+    entry, so pruning must happen on attach (stale entries pinned device memory forever)."""
+    import torch
+    from mepol_b200 import entropy as E
+
+    class FakeHandle:
+        k1 = 5
+    E._handles.clear()
+    keep = []
+    for i in range(50):
+        t = torch.zeros((4, 5), dtype=torch.int64)
+        E.attach_handle(t, FakeHandle())
+        if i % 10 == 0:
+            keep.append(t)                     # a few stay alive, most die at once
+        assert len(E._handles) <= E._CACHE_CAP
+    del keep
+    t = torch.zeros((4, 5), dtype=torch.int64)
+    E.attach_handle(t, FakeHandle())
+    assert len(E._handles) <= E._CACHE_CAP
+    assert E._handles[(id(t), 5)][0]() is t
+    E._handles.clear()
