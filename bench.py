@@ -554,9 +554,17 @@ def run_ours(args):
             _lib.check(lib.mepol_iw_entropy_bwd_f32(c_b.data_ptr(), gw_b.data_ptr(), sc_b.data_ptr(), off_dev.data_ptr(),
                                                     n_traj, n, rowptr.data_ptr(), col.data_ptr(), one_b.data_ptr(),
                                                     gr_b.data_ptr(), sp), "bwd")
+        def k_fused():
+            _lib.check(lib.mepol_iw_entropy_fwd_bwd_f32(ltd.data_ptr(), lb_dev.data_ptr(), off_dev.data_ptr(), n_traj, n,
+                                                        handle.idx.data_ptr(), k1, rk32.data_ptr(), d, math.log(G), B, 0.0,
+                                                        rowptr.data_ptr(), col.data_ptr(), c_b.data_ptr(), gw_b.data_ptr(),
+                                                        sc_b.data_ptr(), gr_b.data_ptr(), ws_b.data_ptr(), ws_b.numel(), sp),
+                       "fwd_bwd")
         k_fwd()
         comp["iw_kernels_fwd_ms"] = t_of(k_fwd, 20)
         comp["iw_kernels_bwd_ms"] = t_of(k_bwd, 20)
+        # one C-ABI call for forward + backward (what the autograd bridge issues), buffers pre-allocated
+        comp["iw_fused_call_ms"] = t_of(k_fused, 20)
         if world == 1:
             comp["search_ms"] = t_of(lambda: searcher(shard_dev), 2)
             comp["search_stats"] = {k_: int(v) for k_, v in zip(("candidates", "fallback_rows", "compactions"),
@@ -564,6 +572,7 @@ def run_ours(args):
             # the epoch-realistic mix of the reference's off-policy loop -- one search per epoch and
             # max_off_iters = 30 objective evaluations (forward + backward) on the same particles
             comp["epoch_mix_states_per_s"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fwd_bwd_ms"]) * 1e-3)
+            comp["epoch_mix_states_per_s_c_abi"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fused_call_ms"]) * 1e-3)
     # live launch count of one step (rank 0 launches the objective as well as its share of the search)
     if world > 1:
         dist.barrier()

@@ -116,7 +116,7 @@ int mepol_rev_csr(const int32_t *idx, int64_t n, int k1, int32_t *rowptr, int32_
  *     reference's eps argument (0 for every shipped config but MountainCar's 1e-15).
  * Outputs (device): c [n] stabilised log-weights (cumsum), gW [n] dH/dW_i (may be NULL when no
  * backward is needed), scal double[8] = {H, KL_raw, s=sum_i gW_i*W_i, M=max c, S=sum exp(c-M),
- * n_nan_or_inf_terms, float64-exp range flag, 0}.
+ * n_nan_or_inf_terms, float64-exp range flag, 1.0 (the unit upstream gradient of the fused call below)}.
  * The _f32 form stores c/gW in float32 and evaluates per-row terms in fp32 with fp64 accumulation;
  * the _f64 form is float64 end to end (what the drop-in uses to reproduce the float64 reference).
  */
@@ -142,6 +142,21 @@ int mepol_iw_entropy_bwd_f64(const double *c, const double *gW, const double *sc
                              const int32_t *traj_off, int64_t n_traj, int64_t n,
                              const int32_t *rowptr, const int32_t *col, const double *grad_H,
                              double *grad_logp_t, void *stream);
+
+/* Forward + backward in one call (the backward for dH = 1; scale grad_unit by the upstream gradient):
+ * what the autograd bridge issues when a gradient will be asked for (policy_update, mepol.py:268-281).
+ * Same kernels and bit-identical results as mepol_iw_entropy_fwd_* followed by mepol_iw_entropy_bwd_*. */
+int mepol_iw_entropy_fwd_bwd_f32(const float *logp_t, const float *logp_b, const int32_t *traj_off,
+                                 int64_t n_traj, int64_t n, const int32_t *idx, int k1, const float *rk,
+                                 int ns, double log_G, double B, double eps, const int32_t *rowptr,
+                                 const int32_t *col, float *c, float *gW, double *scal, float *grad_unit,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+int mepol_iw_entropy_fwd_bwd_f64(const double *logp_t, const double *logp_b, const int32_t *traj_off,
+                                 int64_t n_traj, int64_t n, const int32_t *idx, int k1,
+                                 const double *rk, int ns, double log_G, double B, double eps,
+                                 const int32_t *rowptr, const int32_t *col, double *c, double *gW,
+                                 double *scal, double *grad_unit, void *workspace,
+                                 size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,10 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _sz, _vp]),
     "mepol_iw_entropy_fwd_f64": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _dbl, _dbl, _dbl,
                                         _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mepol_iw_entropy_fwd_bwd_f32": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _dbl, _dbl, _dbl,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mepol_iw_entropy_fwd_bwd_f64": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _dbl, _dbl, _dbl,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mepol_iw_entropy_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mepol_iw_entropy_bwd_f64": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -22,6 +22,8 @@
 //              backward needs no grid-wide dependency.
 // Algorithmic HBM bytes per state at k=4, fp32 storage: scan 12, gather 8+8k+... see
 // DESIGN.md section "IW kernels".
+#include <math.h>
+
 #include "common.cuh"
 
 namespace mepol {
@@ -198,15 +200,15 @@ __global__ void __launch_bounds__(kGatherThreads)
     iw_gather_kernel(const T *__restrict__ c, const int32_t *__restrict__ idx, int k1, int n,
                      const T *__restrict__ rk, int ns, double log_G, double B, double eps,
                      T *__restrict__ gW, double *__restrict__ blk_part, unsigned *__restrict__ counters,
-                     double *__restrict__ scal) {
+                     double *__restrict__ scal, double log_k_over_n, double logV_const) {
     __shared__ double s_warp[32];
     __shared__ unsigned s_ticket;
     const int k = k1 - 1;
     const double M = scal[3], S = scal[4];
     // per-thread constants, amortised over kGatherRows rows
     const double inv_S = 1.0 / S, inv_k = 1.0 / (double)k;
-    const double log_k_over_n = log((double)k) - log((double)n);
-    const double logV_const = 0.5 * (double)ns * kLogPi - log_G;
+    // log_k_over_n = log k - log n and logV_const = (ns/2) log pi - lgamma(ns/2+1) come from the host: two
+    // float64 logs per thread were a quarter of this kernel's instructions
     const T Mt = (T)M;
     double h_term = 0.0, kl_term = 0.0, s_term = 0.0, bad = 0.0;
     // gather phase first for every row of the thread: kGatherRows * k independent loads in flight
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kGatherThreads)
         scal[1] = a1 / (double)n + poison;   // KL before the max(0, .) clamp
         scal[2] = a2;                 // s = sum_i gW_i W_i
         scal[5] = a3;                 // rows whose terms were nan/inf
-        scal[7] = 0.0;
+        scal[7] = 1.0;                // unit upstream gradient for the fused forward+backward entry point
     }
 }
 
@@ -717,7 +719,8 @@ static int iw_fwd_impl(const T *lt, const T *lb, const int32_t *traj_off, int64_
         iw_scan_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(lt, lb, traj_off, (int)n_traj, c, w.traj_max,
                                                                 w.traj_sum, w.counters, scal);
     iw_gather_kernel<T><<<gather_blocks_for(n), kGatherThreads, 0, st>>>(
-        c, idx, k1, (int)n, rk, ns, log_G, B, eps, gW, w.blk_part, w.counters, scal);
+        c, idx, k1, (int)n, rk, ns, log_G, B, eps, gW, w.blk_part, w.counters, scal,
+        log((double)(k1 - 1)) - log((double)n), 0.5 * (double)ns * kLogPi - log_G);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }
@@ -755,6 +758,36 @@ extern "C" int mepol_iw_entropy_fwd_f64(const double *logp_t, const double *logp
                                         double *scal, void *workspace, size_t workspace_bytes, void *stream) {
     return iw_fwd_impl<double>(logp_t, logp_b, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, c, gW, scal,
                                workspace, workspace_bytes, stream);
+}
+// Forward and backward in one call, the backward for dH = 1 (scal[7] holds the 1.0 it reads as grad_H):
+// what an autograd bridge wants when it knows a gradient will be asked for -- the caller scales
+// grad_unit by the incoming dH afterwards.  Same kernels, same results as the two separate calls.
+template <typename T>
+static int iw_fwd_bwd_impl(const T *lt, const T *lb, const int32_t *traj_off, int64_t n_traj, int64_t n,
+                           const int32_t *idx, int k1, const T *rk, int ns, double log_G, double B, double eps,
+                           const int32_t *rowptr, const int32_t *col, T *c, T *gW, double *scal, T *grad_unit,
+                           void *workspace, size_t workspace_bytes, void *stream) {
+    MEPOL_REQUIRE(gW && grad_unit && rowptr && col, MEPOL_E_INVALID, "iw_entropy_fwd_bwd: null pointer");
+    int rc = iw_fwd_impl<T>(lt, lb, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, c, gW, scal, workspace,
+                            workspace_bytes, stream);
+    if (rc != MEPOL_OK) return rc;
+    return iw_bwd_impl<T>(c, gW, scal, traj_off, n_traj, n, rowptr, col, scal + 7, grad_unit, stream);
+}
+extern "C" int mepol_iw_entropy_fwd_bwd_f32(const float *logp_t, const float *logp_b, const int32_t *traj_off,
+                                            int64_t n_traj, int64_t n, const int32_t *idx, int k1, const float *rk,
+                                            int ns, double log_G, double B, double eps, const int32_t *rowptr,
+                                            const int32_t *col, float *c, float *gW, double *scal, float *grad_unit,
+                                            void *workspace, size_t workspace_bytes, void *stream) {
+    return iw_fwd_bwd_impl<float>(logp_t, logp_b, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, rowptr, col, c,
+                                  gW, scal, grad_unit, workspace, workspace_bytes, stream);
+}
+extern "C" int mepol_iw_entropy_fwd_bwd_f64(const double *logp_t, const double *logp_b, const int32_t *traj_off,
+                                            int64_t n_traj, int64_t n, const int32_t *idx, int k1, const double *rk,
+                                            int ns, double log_G, double B, double eps, const int32_t *rowptr,
+                                            const int32_t *col, double *c, double *gW, double *scal,
+                                            double *grad_unit, void *workspace, size_t workspace_bytes, void *stream) {
+    return iw_fwd_bwd_impl<double>(logp_t, logp_b, traj_off, n_traj, n, idx, k1, rk, ns, log_G, B, eps, rowptr, col, c,
+                                   gW, scal, grad_unit, workspace, workspace_bytes, stream);
 }
 extern "C" int mepol_iw_entropy_bwd_f32(const float *c, const float *gW, const double *scal,
                                         const int32_t *traj_off, int64_t n_traj, int64_t n,

@@ -21,7 +21,7 @@
 // fp16 accumulation and exactness.  The accumulator is rounded to fp16 after each of the two K = 16
 // steps, and inside a step the 17 addends are aligned to the largest one.  With D1 the value after the
 // first step (|D1| <= c = 2 ||x~_A|| ||y~_A||, A = the first 16 columns), M1, M2 the largest addend of
-// each step, u_r = 2^-10 (one fp16 ulp) and u_i = 2^-12:
+// each step, u_r = 2^-10 (one fp16 ulp) and u_i = 2^-20:
 //     |s~ - s| <= err(s~) = e0 + u_r (c + |s~|) + u_i (M1 + M2),
 // e0 = the operand-rounding bound of tc_band().  err is monotone in s~, so with t the k1-th smallest
 // score seen, every reference with s~ > tau(t) = t + [2 e0 + 2 u_r (c + |t|) + 2 u_i (M1 + M2)] / (1 - u_r)
@@ -82,9 +82,10 @@ template <int NC> constexpr uint32_t t2_idesc() {
 // scripts/exp_tc2.py, pinned by tests/test_gpu_tc.py; each constant is TWICE what was observed, and the
 // band costs < 1 % of the kernel per doubling):
 //   rounding of the accumulator: round-to-nearest, <= 0.5 ulp of the step's result -> assume 1 ulp = 2^-10 |result|
-//   internal alignment of the 17 addends: <= 2^-13 of the step's largest addend   -> assume 2^-12 of it
+//   internal alignment of the 17 addends: <= 2^-25 of the step's largest addend   -> assume 2^-20 of it
+//   (i.e. the sum inside a step is formed at fp32-like precision; only the stored result is fp16)
 constexpr float kT2Ulp = 9.765625e-4f;               // 2^-10
-constexpr float kT2Align = 2.44140625e-4f;           // 2^-12
+constexpr float kT2Align = 9.5367431640625e-7f;      // 2^-20
 
 __device__ __forceinline__ uint32_t hmin2_3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import entropy as _entropy
-from .knn import knn_device, to_host
+from .knn import knn_device, to_device_f32, to_host
 
 _ORIGINALS = {}
 _REPLACED = ("collect_particles_and_compute_knn", "compute_importance_weights", "compute_entropy",
@@ -65,8 +65,8 @@ def search_particles(next_states, k):
     if not np.isfinite(x).all():
         raise ValueError("Input contains NaN or infinity")
     dev = _entropy._device()
-    xt = torch.from_numpy(x).pin_memory().to(dev, non_blocking=True)
     with torch.cuda.device(dev):
+        xt = to_device_f32(x, dev)
         res = knn_device(xt, k + 1)
         distances, indices = to_host(res)
     handle = _entropy.SearchHandle(res.indices, res.rk, k + 1)

@@ -54,6 +54,17 @@ def _device():
     return _config["device"] or torch.device("cuda", torch.cuda.current_device())
 
 
+import contextlib
+
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on(dev):
+    """Context that makes `dev` current -- free when it already is (the guard costs ~10 us per call, a
+    tenth of the whole objective at small batch sizes)."""
+    return _NULL_CTX if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+
 # ------------------------------------------------------------------------------- device handles
 class SearchHandle:
     """Device-resident view of one k-NN search result, shared by every objective evaluation of an
@@ -67,11 +78,25 @@ class SearchHandle:
         self._rk = {torch.float64: rk_f64.contiguous()}
         self._csr = None
         self._ws = None
+        self._scratch = {}
 
     def rk(self, dtype):
         if dtype not in self._rk:
             self._rk[dtype] = self._rk[torch.float64].to(dtype)
         return self._rk[dtype]
+
+    def scratch(self, dtype, n_traj):
+        """(c, gW, workspace) of the objective kernels for this search result: intermediates that never
+        leave a forward/backward call, allocated once per (dtype, trajectory count) and reused."""
+        key = (dtype, int(n_traj))
+        hit = self._scratch.get(key)
+        if hit is None:
+            dev = self.idx.device
+            with torch.cuda.device(dev):
+                hit = (torch.empty(self.n, dtype=dtype, device=dev), torch.empty(self.n, dtype=dtype, device=dev),
+                       torch.empty(_lib.iw_workspace_bytes(self.n, n_traj), dtype=torch.uint8, device=dev))
+            self._scratch = {key: hit}
+        return hit
 
     def csr(self):
         if self._csr is None:
@@ -100,8 +125,14 @@ def traj_offsets(real_traj_lengths, device):
 class IWEntropyFunction(torch.autograd.Function):
     """(H, KL_raw, n_bad) = f(logp_target, logp_behav) through the fused CUDA kernels.
 
-    forward  -> mepol_iw_entropy_fwd_{f32,f64}   (replaces mepol.py:121-152 and :159-165)
-    backward -> mepol_iw_entropy_bwd_{f32,f64}   (replaces autograd of the same lines)"""
+    forward  -> mepol_iw_entropy_fwd_{f32,f64}       (replaces mepol.py:121-152 and :159-165), or, when a
+                gradient will be asked for, mepol_iw_entropy_fwd_bwd_{f32,f64}: forward AND backward for
+                dH = 1 in ONE library call (the objective is launch/host bound at every batch size)
+    backward -> one multiply by the incoming dH (replaces autograd of the same lines, mepol.py:278)
+
+    Scratch that never leaves the call (c, gW, the reduction workspace) lives on the SearchHandle and is
+    reused by every evaluation of the epoch; only what the caller can keep (the scalars, the gradient)
+    is allocated per call."""
 
     @staticmethod
     def forward(ctx, logp_t, logp_b, handle, traj_off, n_traj, k, ns, log_G, B, eps):
@@ -111,7 +142,10 @@ class IWEntropyFunction(torch.autograd.Function):
         if dt not in (torch.float32, torch.float64):
             raise ValueError("log-probs must be float32 or float64")
         lt = logp_t.detach().contiguous()
-        lb = logp_b.detach().to(dt).contiguous()
+        lb = logp_b.detach()
+        if lb.dtype != dt:
+            lb = lb.to(dt)
+        lb = lb.contiguous()
         n = lt.numel()
         if n != handle.n or handle.k1 != k + 1:
             raise ValueError(f"log-probs ({n}) do not match the search result ({handle.n} rows, k1={handle.k1})")
@@ -119,38 +153,36 @@ class IWEntropyFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:2])
         lib = _lib.load()
         suffix = "f32" if dt == torch.float32 else "f64"
-        with torch.cuda.device(dev):
-            c = torch.empty(n, dtype=dt, device=dev)
-            gW = torch.empty(n, dtype=dt, device=dev) if need_grad else None
+        with _on(dev):
+            c, gW, ws = handle.scratch(dt, n_traj)
             scal = torch.empty(8, dtype=torch.float64, device=dev)
-            ws = torch.empty(_lib.iw_workspace_bytes(n, n_traj), dtype=torch.uint8, device=dev)
-            fn = getattr(lib, "mepol_iw_entropy_fwd_" + suffix)
-            rc = fn(lt.data_ptr(), lb.data_ptr(), traj_off.data_ptr(), n_traj, n, handle.idx.data_ptr(),
-                    handle.k1, handle.rk(dt).data_ptr(), int(ns), float(log_G), float(B), float(eps),
-                    c.data_ptr(), gW.data_ptr() if need_grad else None, scal.data_ptr(), ws.data_ptr(),
-                    ws.numel(), _stream_ptr(dev))
-            _lib.check(rc, "mepol_iw_entropy_fwd_" + suffix)
-        ctx.handle, ctx.traj_off, ctx.n_traj, ctx.suffix = handle, traj_off, n_traj, suffix
-        ctx.save_for_backward(c, gW if need_grad else c, scal)
-        ctx.keep = ws
-        H, kl_raw, n_bad = scal[0].clone(), scal[1].clone(), scal[5].clone()
+            if need_grad:
+                rowptr, col = handle.csr()
+                unit = torch.empty(n, dtype=dt, device=dev)
+                fn = getattr(lib, "mepol_iw_entropy_fwd_bwd_" + suffix)
+                rc = fn(lt.data_ptr(), lb.data_ptr(), traj_off.data_ptr(), n_traj, n, handle.idx.data_ptr(),
+                        handle.k1, handle.rk(dt).data_ptr(), int(ns), float(log_G), float(B), float(eps),
+                        rowptr.data_ptr(), col.data_ptr(), c.data_ptr(), gW.data_ptr(), scal.data_ptr(),
+                        unit.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc, "mepol_iw_entropy_fwd_bwd_" + suffix)
+                ctx.unit = unit
+            else:
+                fn = getattr(lib, "mepol_iw_entropy_fwd_" + suffix)
+                rc = fn(lt.data_ptr(), lb.data_ptr(), traj_off.data_ptr(), n_traj, n, handle.idx.data_ptr(),
+                        handle.k1, handle.rk(dt).data_ptr(), int(ns), float(log_G), float(B), float(eps),
+                        c.data_ptr(), None, scal.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc, "mepol_iw_entropy_fwd_" + suffix)
+                ctx.unit = None
+        # views of the per-call scalar block (no copy kernels); the block is owned by these outputs
+        H, kl_raw, n_bad = scal[0], scal[1], scal[5]
         ctx.mark_non_differentiable(kl_raw, n_bad)
         return H, kl_raw, n_bad
 
     @staticmethod
     def backward(ctx, grad_H, _gkl, _gbad):
-        c, gW, scal = ctx.saved_tensors
-        handle = ctx.handle
-        dev = c.device
-        n = c.numel()
-        rowptr, col = handle.csr()
-        g = grad_H.detach().to(torch.float64).reshape(1).contiguous()
-        with torch.cuda.device(dev):
-            out = torch.empty(n, dtype=c.dtype, device=dev)
-            fn = getattr(_lib.load(), "mepol_iw_entropy_bwd_" + ctx.suffix)
-            rc = fn(c.data_ptr(), gW.data_ptr(), scal.data_ptr(), ctx.traj_off.data_ptr(), ctx.n_traj, n,
-                    rowptr.data_ptr(), col.data_ptr(), g.data_ptr(), out.data_ptr(), _stream_ptr(dev))
-            _lib.check(rc, "mepol_iw_entropy_bwd_" + ctx.suffix)
+        if ctx.unit is None:
+            raise RuntimeError("mepol_b200: the objective was evaluated without gradient tracking")
+        out = ctx.unit * grad_H          # dH/d logp_target (0-dim dH does not change the storage dtype)
         g_t = out if ctx.needs_input_grad[0] else None
         g_b = -out if ctx.needs_input_grad[1] else None
         return g_t, g_b, None, None, None, None, None, None, None, None
@@ -354,6 +386,7 @@ class _StaticHandle:
         self.idx, self.k1, self.n = torch.empty_like(handle.idx), handle.k1, handle.n
         self._rk = torch.empty_like(handle.rk(dt))
         self._csr = None
+        self._scr = None
         if want_grad:          # the reverse CSR only serves the backward: KL / no_grad graphs never build it
             rowptr, col = handle.csr()
             self._csr = (torch.empty_like(rowptr), torch.empty_like(col))
@@ -371,6 +404,13 @@ class _StaticHandle:
 
     def csr(self):
         return self._csr
+
+    def scratch(self, dtype, n_traj):
+        if self._scr is None:        # first (warm-up) run, outside the capture: the buffers persist
+            dev = self.idx.device
+            self._scr = (torch.empty(self.n, dtype=dtype, device=dev), torch.empty(self.n, dtype=dtype, device=dev),
+                         torch.empty(_lib.iw_workspace_bytes(self.n, n_traj), dtype=torch.uint8, device=dev))
+        return self._scr
 
 
 class _StaticBatch:

@@ -74,32 +74,61 @@ def knn_device(ref, k1, queries=None, algo=_lib.KNN_AUTO, workspace=None, out=No
     return res
 
 
-_STAGE = None            # persistent pinned staging block (grown geometrically), guarded by _STAGE_LOCK
-_STAGE_LOCK = threading.Lock()
+class _PinnedStage:
+    """One persistent pinned host block (grown geometrically) + the event of the last transfer that
+    used it.  Allocating pinned memory per call costs milliseconds -- more than a whole search at the
+    reference's batch sizes -- and a pageable source/destination makes the driver stage the copy itself."""
+
+    def __init__(self):
+        self.buf = None
+        self.busy = None
+        self.lock = threading.Lock()
+
+    def take(self, nbytes):
+        if self.busy is not None:          # the previous transfer through this block must have drained
+            self.busy.synchronize()
+            self.busy = None
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(nbytes, 1 << 20, 0 if self.buf is None else 2 * self.buf.numel()),
+                                   dtype=torch.uint8, pin_memory=True)
+        return self.buf
+
+    def mark(self, device):
+        self.busy = torch.cuda.Event()
+        self.busy.record(torch.cuda.current_stream(device))
 
 
-def _stage(nbytes):
-    global _STAGE
-    if _STAGE is None or _STAGE.numel() < nbytes:
-        _STAGE = torch.empty(max(nbytes, 1 << 20, 0 if _STAGE is None else 2 * _STAGE.numel()),
-                             dtype=torch.uint8, pin_memory=True)
-    return _STAGE
+_STAGE_IN, _STAGE_OUT = _PinnedStage(), _PinnedStage()
+
+
+def to_device_f32(x, device):
+    """Host float32 [n, d] numpy array -> device tensor through the persistent pinned input block
+    (replaces the per-call `torch.from_numpy(x).pin_memory()` of round 1: rollout output staging,
+    reference mepol.py:187,195-200)."""
+    nbytes = x.nbytes
+    with _STAGE_IN.lock:
+        pin = _STAGE_IN.take(nbytes)[:nbytes].view(torch.float32).view(x.shape)
+        pin.copy_(torch.from_numpy(x))                     # host memcpy into pinned memory
+        xt = torch.empty(x.shape, dtype=torch.float32, device=device)
+        xt.copy_(pin, non_blocking=True)
+        _STAGE_IN.mark(device)
+    return xt
 
 
 def to_host(res):
     """(distances float64, indices int64) of a KnnResult as fresh CPU tensors owned by the caller.
-    The device->host copies go through ONE persistent pinned block (a pageable destination makes the
-    driver stage the copy itself and costs ~3x more at GridWorld's [24000, 51] outputs; allocating
-    pinned memory per call costs milliseconds), then a host memcpy into the returned tensors."""
+    The device->host copies go through ONE persistent pinned block; the indices cross the bus as int32
+    and are widened to sklearn's int64 by the host while it makes the caller's copy (half the bytes, no
+    widening kernel, no extra clone)."""
     n = res.distances.numel()
-    with _STAGE_LOCK:
-        st = _stage(16 * n)
+    with _STAGE_OUT.lock:
+        st = _STAGE_OUT.take(12 * n)
         d_pin = st[:8 * n].view(torch.float64).view(res.distances.shape)
-        i_pin = st[8 * n:16 * n].view(torch.int64).view(res.indices.shape)
+        i_pin = st[8 * n:12 * n].view(torch.int32).view(res.indices.shape)
         d_pin.copy_(res.distances, non_blocking=True)
-        i_pin.copy_(res.indices.to(torch.int64), non_blocking=True)
+        i_pin.copy_(res.indices, non_blocking=True)
         torch.cuda.current_stream(res.indices.device).synchronize()
-        return d_pin.clone(), i_pin.clone()
+        return d_pin.clone(), i_pin.to(torch.int64)
 
 
 def knn(next_states, k, algo=_lib.KNN_AUTO, device=None):
@@ -113,8 +142,8 @@ def knn(next_states, k, algo=_lib.KNN_AUTO, device=None):
     if not torch.cuda.is_available():
         raise _lib.MepolError("mepol_b200.knn needs a CUDA device (there is no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    xt = torch.from_numpy(x).pin_memory().to(dev, non_blocking=True)
     with torch.cuda.device(dev):
+        xt = to_device_f32(x, dev)
         res = knn_device(xt, k + 1, algo=algo)
         dist, idx = to_host(res)
     return dist.numpy(), idx.numpy()

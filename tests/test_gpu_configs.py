@@ -97,3 +97,62 @@ def test_config_shapes_match_oracle(cfg):
         np.testing.assert_allclose(got / sc, val / sc, rtol=0, atol=1e-8)
     sc = np.abs(g_ref["log_std"]).max() + 1e-300
     np.testing.assert_allclose(named["log_std"].grad.numpy() / sc, g_ref["log_std"] / sc, rtol=0, atol=1e-8)
+
+
+FULL = [("ant_full", 100, 500, 29, 8, [400, 300], 7, 4, 0.0, "normal"),
+        ("grid_world_full", 100, 1200, 2, 2, [300, 300], 2, 50, 0.0, "uniform6"),
+        ("mountain_car_full", 100, 400, 2, 1, [300, 300], 2, 4, 1e-15, "mountaincar")]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=[c[0] for c in FULL])
+def test_full_entropy_evaluation_call_shape(cfg):
+    """The full-entropy evaluation of the reference loop (mepol.py:347-354 and :512-519): 5x the batch
+    (num_traj * full_entropy_traj_scale), `full_entropy_k`, the SAME policy object passed as behavioural
+    and target, under no_grad.  The weights are then exactly 1/N; checked against the oracle, against a
+    second call (the behavioural cache must not confuse the two roles), and the result carries no graph."""
+    name, T, L, F, A, hidden, ns, k, eps, kind = cfg
+    rng = np.random.default_rng(abs(hash(name)) % 2**31)
+    states = rng.standard_normal((T, L + 1, F)).astype(np.float32)
+    if kind == "uniform6":
+        states[..., :2] = rng.uniform(-6, 6, (T, L + 1, 2))
+    elif kind == "mountaincar":
+        states[..., 0] = rng.uniform(-1.2, 0.6, (T, L + 1))
+        states[..., 1] = rng.uniform(-0.07, 0.07, (T, L + 1))
+    actions = (0.6 * rng.standard_normal((T, L, A))).astype(np.float32)
+    lens = np.full((T, 1), L, dtype=np.int64)
+    next_states = np.ascontiguousarray(states[:, 1:, :ns].reshape(-1, ns))
+    n = T * L
+    dist, idx, _ = mepol_b200.search_particles(next_states, k)
+    rows = np.sort(rng.choice(n, 512, replace=False))
+    ref_d, ref_i = knn_oracle.knn_c(next_states, k + 1, queries=next_states[rows], mode="kd_tree")
+    np.testing.assert_array_equal(idx.numpy()[rows], ref_i)
+    np.testing.assert_allclose(dist.numpy()[rows], ref_d, rtol=1e-12)
+
+    torch.manual_seed(1)
+    pol = _Policy(hidden, F, A)
+    G = float(scipy.special.gamma(ns / 2 + 1))
+    full_B = float(np.log(k) - scipy.special.digamma(k))
+    t_states, t_actions = torch.tensor(states, dtype=torch.float64), torch.tensor(actions, dtype=torch.float64)
+    t_lens = torch.tensor(lens)
+    state0 = torch.get_rng_state()
+    with torch.no_grad():
+        ent = mepol_b200.compute_entropy(pol, pol, t_states, t_actions, T, t_lens, dist, idx, k, G, full_B, ns, eps)
+        ent2 = mepol_b200.compute_entropy(pol, pol, t_states, t_actions, T, t_lens, dist, idx, k, G, full_B, ns, eps)
+    assert ent.device.type == "cpu" and ent.dtype == torch.float64 and not ent.requires_grad
+    assert torch.equal(ent, ent2)
+    # quirk Q7: two get_log_p calls per trajectory burn randn(L, A) each from the global generator
+    torch.set_rng_state(state0)
+    for _ in range(2):
+        for _t in range(T):
+            for _c in range(2):
+                torch.randn((L, A), dtype=torch.float64)
+    expect_state = torch.get_rng_state()
+    torch.set_rng_state(state0)
+    with torch.no_grad():
+        mepol_b200.compute_entropy(pol, pol, t_states, t_actions, T, t_lens, dist, idx, k, G, full_B, ns, eps)
+        mepol_b200.compute_entropy(pol, pol, t_states, t_actions, T, t_lens, dist, idx, k, G, full_B, ns, eps)
+    assert torch.equal(torch.get_rng_state(), expect_state)
+    zeros = np.zeros(n)
+    H_ref = O.entropy(zeros, zeros, lens.reshape(-1), dist.numpy(), idx.numpy(), k, G, full_B, ns, eps)
+    assert math.isfinite(H_ref)
+    np.testing.assert_allclose(ent.item(), H_ref, rtol=1e-10)
