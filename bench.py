@@ -360,7 +360,7 @@ def run_ours(args):
     import mepol_b200
     from mepol_b200 import _lib
     from mepol_b200 import entropy as E
-    from mepol_b200.dist import ShardedSearch, shard_bounds
+    from mepol_b200.dist import ShardedSearch, SharedHostResults, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -390,9 +390,9 @@ def run_ours(args):
     lb_dev = lb_pin.to(dev)
     off_dev, _ = mepol_b200.traj_offsets(lens, dev)
     searcher = ShardedSearch(n, d, k1, dev, algo=algo)
-    idx_host = torch.empty((n, k1), dtype=torch.int32).pin_memory() if rank == 0 else None
-    idx_host64 = torch.empty((n, k1), dtype=torch.int64) if rank == 0 else None
-    dist_host = torch.empty((n, k1), dtype=torch.float64).pin_memory() if rank == 0 else None
+    # sklearn's output arrays on the host (indices int64, distances float64): one page-locked shared-memory
+    # block that every rank's GPU writes its own rows into (G concurrent PCIe transfers)
+    host_results = None if args.no_e2e else SharedHostResults(n, k1, device=dev)
     grad_host = torch.empty((n,), dtype=torch.float32).pin_memory() if rank == 0 else None
     scal_host = torch.empty((2,), dtype=torch.float64).pin_memory() if rank == 0 else None
     copy_stream = torch.cuda.Stream(device=dev)
@@ -412,31 +412,29 @@ def run_ours(args):
         return None
 
     def step_e2e():
-        sh = x_pin.to(dev, non_blocking=True)                                   # H2D particles
-        idx_full, rk_full, dist_full = searcher(sh, gather_distances=True)
-        if rank != 0:
-            return None
-        # the neighbour lists go back to the host on a copy stream while the objective runs: int32 over
-        # the bus, widened to sklearn's int64 by the host (half the bytes, no device widening kernel)
+        sh = x_pin.to(dev, non_blocking=True)                                   # H2D particles (own shard)
+        idx_full, rk_full, _ = searcher(sh)
+        # every rank sends the rows it searched to the host arrays on a copy stream (D2H indices as int64 +
+        # distances float64: 16 * k1 bytes per row), while rank 0 goes on with the objective
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
-            idx_host.copy_(idx_full, non_blocking=True)                         # D2H indices (int32)
-            dist_host.copy_(dist_full, non_blocking=True)                       # D2H distances (float64)
-        ltt = lt_pin.to(dev, non_blocking=True).requires_grad_(True)             # H2D log-probs
-        lbt = lb_pin.to(dev, non_blocking=True)
-        H, kl_raw, g = objective(idx_full, rk_full, ltt, lbt)
-        grad_host.copy_(g, non_blocking=True)                                   # D2H gradient
-        scal_host.copy_(torch.stack([H.detach(), kl_raw]), non_blocking=True)   # D2H entropy, KL
+            host_results.push(searcher.own_idx, searcher.own_dist)
+        if rank == 0:
+            ltt = lt_pin.to(dev, non_blocking=True).requires_grad_(True)         # H2D log-probs
+            lbt = lb_pin.to(dev, non_blocking=True)
+            H, kl_raw, g = objective(idx_full, rk_full, ltt, lbt)
+            grad_host.copy_(g, non_blocking=True)                               # D2H gradient
+            scal_host.copy_(torch.stack([H.detach(), kl_raw]), non_blocking=True)   # D2H entropy, KL
         copy_stream.synchronize()
-        idx_host64.copy_(idx_host)                                              # sklearn's dtype, on the host
         torch.cuda.current_stream().synchronize()
-        torch.cuda.current_stream().wait_stream(copy_stream)
+        if world > 1:
+            dist.barrier()                                                      # all rows have landed on the host
         return scal_host
 
-    h2d = (hi - lo) * d * 4 + (2 * n * 4 if rank == 0 else 0)
-    d2h = n * k1 * 12 + n * 4 + 16
+    h2d = n * d * 4 + 2 * n * 4                     # all ranks' shards + the log-probs on rank 0
+    d2h = n * k1 * 16 + n * 4 + 16                  # all ranks' result rows + gradient and scalars on rank 0
 
     def barrier():
         torch.cuda.synchronize()
@@ -494,6 +492,12 @@ def run_ours(args):
     parity = None
     if not args.no_verify:
         idx_full, rk_full, dist_full = searcher(shard_dev, gather_distances=True)
+        if host_results is not None and rank == 0:
+            # the e2e arm's host arrays (written by all ranks in the last e2e step) against the device result
+            host_ok = bool((host_results.indices == idx_full.cpu().to(torch.int64)).all()) and \
+                bool((host_results.distances == dist_full.cpu()).all())
+        else:
+            host_ok = None
         if world > 1 and rank == 0:
             # the same array searched by ONE GPU (rank 0, all rows): the sharded result must be bit-identical
             full_dev = searcher.full
@@ -501,10 +505,10 @@ def run_ours(args):
             mism = int((single.indices != idx_full).any(dim=1).sum().item())
             mism_rk = int((single.rk != rk_full).sum().item())
             parity = {"vs": "single-GPU search of the same array on rank 0 (bitwise)", "rows_checked": n,
-                      "mismatch": mism, "rk_mismatch": mism_rk}
+                      "mismatch": mism, "rk_mismatch": mism_rk, "host_arrays_equal_device_result": host_ok}
             del single
         elif world == 1:
-            parity = {"vs": None, "rows_checked": 0, "mismatch": None}
+            parity = {"vs": None, "rows_checked": 0, "mismatch": None, "host_arrays_equal_device_result": host_ok}
         if world > 1:
             dist.barrier()
 
@@ -632,7 +636,8 @@ def run_ours(args):
             far = dist_s > 1e-3                                         # col 0 (self) is ~1e-7 in sklearn's brute form
             rel = float(np.max(np.abs(got_d[far] - dist_s[far]) / dist_s[far]))
             parity = {"vs": "sklearn NearestNeighbors on the benchmarked array (the CPU leg's sampled rows)",
-                      "rows_checked": int(rows), "mismatch": bad_rows, "max_rel_dist_err": rel, "dist_rtol": 1e-5}
+                      "rows_checked": int(rows), "mismatch": bad_rows, "max_rel_dist_err": rel, "dist_rtol": 1e-5,
+                      "host_arrays_equal_device_result": host_ok}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup_done, "warmup_requested": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

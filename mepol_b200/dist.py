@@ -16,6 +16,11 @@ output is bit-identical for every G.  The IW objective runs on the rank that own
 Works with the `gloo` backend on CPU tensors for the partition/collective logic (tests), where the
 search itself is injected.
 """
+import mmap
+import os
+import uuid
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -45,6 +50,7 @@ class ShardedSearch:
         self._ws = None
         self._out = None
         self.last_idx = self.last_rk = self.last_dist = None
+        self.own_idx = self.own_dist = None
 
     def _cuda_search(self, full, queries):
         res = knn_device(full, self.k1, queries=queries, algo=self.algo, workspace=self._ws, out=self._out)
@@ -67,6 +73,7 @@ class ShardedSearch:
             if _marks is not None:
                 mark(ev())
             idx, dst, rk = self.search_fn(shard, shard)
+            self.own_idx, self.own_dist = idx, dst
             if _marks is not None:
                 mark(ev())
                 mark(ev())
@@ -77,6 +84,7 @@ class ShardedSearch:
         if _marks is not None:
             mark(ev())
         idx, dst, rk = self.search_fn(self.full, self.full[self.lo:self.hi])
+        self.own_idx, self.own_dist = idx, dst           # this rank's rows (for SharedHostResults.push)
         if _marks is not None:
             mark(ev())
         dist.all_gather_into_tensor(self.idx_full, idx.contiguous(), group=self.group)
@@ -110,3 +118,70 @@ class ShardedSearch:
             out["gather_results_ms"] += marks[2].elapsed_time(marks[3]) / reps
             out["prune_kernel_ms"] += (pr[0] if pr else 0.0) / reps
         return out
+
+
+class SharedHostResults:
+    """Host-side landing zone of a sharded search on ONE box: sklearn's output arrays (indices int64
+    [N, k1], distances float64 [N, k1], mepol.py:192) live in one POSIX shared-memory block that every
+    rank maps and page-locks (cudaHostRegister), and each GPU copies the rows it searched straight into
+    it -- G concurrent PCIe transfers of N/G rows each instead of gathering everything on the owner's
+    GPU and pushing 16 * k1 * N bytes through one link.  The owner rank (0) reads the arrays after the
+    barrier.  With one rank this degenerates to a pinned block.  No device-side collective is involved
+    for the distances at all (the objective only needs idx + r_k, which ShardedSearch gathers)."""
+
+    def __init__(self, n, k1, device=None, group=None):
+        self.n, self.k1, self.group = n, k1, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device
+        self.lo, self.hi = shard_bounds(n, self.world, self.rank)
+        nbytes = 16 * n * k1
+        name = [None]
+        if self.rank == 0:
+            name[0] = f"/dev/shm/mepol_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}"
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        self._path = name[0]
+        self._file = open(self._path, "r+b")
+        self._map = mmap.mmap(self._file.fileno(), nbytes)
+        if self.world > 1:
+            dist.barrier(group=group)
+        if self.rank == 0:
+            os.unlink(self._path)               # the mapping keeps the memory alive; nothing is left behind
+        buf = torch.frombuffer(self._map, dtype=torch.uint8)
+        self._registered = False
+        if device is not None and torch.device(device).type == "cuda":
+            rc = torch.cuda.cudart().cudaHostRegister(buf.data_ptr(), nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared result block failed (rc={int(rc)})")
+            self._registered = True
+        self._buf = buf
+        self.indices = buf[:8 * n * k1].view(torch.int64).view(n, k1)
+        self.distances = buf[8 * n * k1:].view(torch.float64).view(n, k1)
+
+    def push(self, idx_rows, dist_rows):
+        """This rank's rows (device or host tensors, [N/G, k1]) -> the shared arrays, asynchronously on
+        the current stream; the int32 -> int64 widening happens on the device in front of the copy."""
+        self.indices[self.lo:self.hi].copy_(idx_rows, non_blocking=True)
+        self.distances[self.lo:self.hi].copy_(dist_rows, non_blocking=True)
+
+    def wait(self):
+        """All ranks' copies have landed (stream sync + barrier)."""
+        if self._registered:
+            torch.cuda.current_stream(self.device).synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        if self._buf is None:
+            return
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self._buf.data_ptr())
+        self.indices = self.distances = self._buf = None
+        try:
+            self._map.close()
+        except BufferError:
+            pass
+        self._file.close()

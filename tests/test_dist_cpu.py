@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mepol_b200.dist import ShardedSearch, shard_bounds
+from mepol_b200.dist import ShardedSearch, SharedHostResults, shard_bounds
 
 
 def _free_port():
@@ -76,3 +76,34 @@ def test_single_rank_path_without_process_group():
     ref_d, ref_i = knn_oracle.knn_c(x.numpy(), k1, mode="kd_tree")
     np.testing.assert_array_equal(idx.numpy(), ref_i)
     np.testing.assert_array_equal(dst.numpy(), ref_d)
+
+
+def _sink_worker(rank, world, port, n, k1, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sink = SharedHostResults(n, k1, device=None)        # CPU: same mapping logic, no page-locking
+        lo, hi = shard_bounds(n, world, rank)
+        rows = torch.arange(lo, hi, dtype=torch.int32).reshape(-1, 1).repeat(1, k1) * 10 + torch.arange(k1, dtype=torch.int32)
+        sink.push(rows, rows.to(torch.float64) / 7.0)
+        sink.wait()
+        if rank == 0:
+            torch.save({"idx": sink.indices.clone(), "dist": sink.distances.clone()}, os.path.join(out_dir, "sink.pt"))
+        dist.barrier()
+        sink.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_results_collects_every_ranks_rows(tmp_path):
+    """Each rank writes the rows it searched into the owner's shared host arrays (the e2e path of
+    bench.py at N > 1): the owner sees all of them, widened to sklearn's int64 / float64."""
+    n, k1, world = 4000, 5, 2
+    port = _free_port()
+    mp.spawn(_sink_worker, args=(world, port, n, k1, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(tmp_path, "sink.pt"))
+    expect = torch.arange(n, dtype=torch.int64).reshape(-1, 1).repeat(1, k1) * 10 + torch.arange(k1)
+    assert got["idx"].dtype == torch.int64 and torch.equal(got["idx"], expect)
+    assert torch.equal(got["dist"], expect.to(torch.float64) / 7.0)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("mepol_b200_")], "shared block left behind"
