@@ -125,33 +125,60 @@ int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cu
 
 int mean_blocks_for(int64_t n_ref) { return (int)((n_ref + kMeanRowsPerBlock - 1) / kMeanRowsPerBlock); }
 
-// One thread per row.  dpad is the SIMT operand width; when xb != nullptr the fp16 tensor-core
-// operand is produced as well (refs: [-2*y~ (d cols), n_hi, n_mid, n_lo, 0...]; queries:
-// [x~ (d cols), 1, 1, 1, 0...]) -- see knn_tc.cu.
-__global__ void __launch_bounds__(128)
+// One thread per row, one CTA per 128 rows (= one tensor-core operand tile).  dpad is the SIMT operand
+// width; when xb != nullptr the fp16 tensor-core operand is produced as well (refs: [-2*y~ (d cols),
+// n_hi, n_mid, n_lo, 0...]; queries: [x~ (d cols), 1, 1, 1, 0...]) -- see knn_tc2.cu.
+// Global traffic is staged through shared memory: the 128 x d input block is read as one contiguous
+// range, each thread packs its row out of / into shared memory, and the SIMT rows (128 x dpad floats,
+// contiguous) and the operand tile (8 KB, contiguous in the UMMA canonical order) leave as coalesced
+// stores.  The thread-per-row global accesses of round 1 (116-byte strided reads, 2-byte scattered
+// stores) made this kernel 8x slower than its bytes: 199 -> see profiles/r02 launch list.
+constexpr int kPackRows = 128;
+__host__ __device__ inline int tc_tile_index(int r, int c) { return ((r >> 3) * 4 + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7); }
+
+__global__ void __launch_bounds__(kPackRows)
     pack_rows_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int d, int dpad,
                      const double *__restrict__ mean, float *__restrict__ xs, float *__restrict__ nrm,
                      float *__restrict__ anorm, uint16_t *__restrict__ xb, float *__restrict__ delta,
                      float *__restrict__ ahalf, float *__restrict__ glob, int is_ref) {
+    extern __shared__ __align__(16) unsigned char pack_smem[];
     __shared__ double smean[MEPOL_MAX_DIM];
-    if (threadIdx.x < d) smean[threadIdx.x] = mean[threadIdx.x];
-    __syncthreads();
+    float *s_in = reinterpret_cast<float *>(pack_smem);                         // [128][d]
+    float *s_xs = s_in + kPackRows * d;                                         // [128][dpad + 1] (padded: no bank conflicts)
+    uint16_t *s_xb = reinterpret_cast<uint16_t *>(s_xs + kPackRows * (dpad + 1));   // [4096] one operand tile
+    const int tid = threadIdx.x;
+    if (tid < d) smean[tid] = mean[tid];
     const double sigma = mean[MEPOL_MAX_DIM];
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * kPackRows;
+    const int nrows = row0 < n ? (int)((n - row0) < kPackRows ? (n - row0) : kPackRows) : 0;
+    {   // contiguous block read (16-byte vectors when the block starts on a 16-byte boundary)
+        const int total = nrows * d;
+        const float *src = x + row0 * d;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {    // a query slice of the fitted matrix may start anywhere
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            float4 *dst4 = reinterpret_cast<float4 *>(s_in);
+            for (int i = tid; i < (total >> 2); i += kPackRows) dst4[i] = src4[i];
+            for (int i = (total & ~3) + tid; i < total; i += kPackRows) s_in[i] = src[i];
+        } else {
+            for (int i = tid; i < total; i += kPackRows) s_in[i] = src[i];
+        }
+    }
+    __syncthreads();
+    const int64_t row = row0 + tid;
+    const int xs_stride = dpad + 1;
     float a_up = 0.f, delta_up = 0.f, atilde_up = 0.f, ahalf_up = 0.f;
     if (row < n) {
-        const float *xr = x + row * d;
-        float *o = xs ? xs + row * dpad : nullptr;
+        const float *xr = s_in + tid * d;
+        float *o = s_xs + tid * xs_stride;
         double n2 = 0.0, dl2 = 0.0, nt2 = 0.0, nh2 = 0.0;
         bool in_range = true;
         for (int c = 0; c < d; ++c) {
             const double v = ((double)xr[c] - smean[c]) * sigma;   // exact: sigma is a power of two
             n2 += v * v;
-            if (o) o[c] = (float)v;
+            o[c] = (float)v;
             in_range = in_range && fabs(v) <= kTcQueryAbsMax;
         }
-        if (o)
-            for (int c = d; c < dpad; ++c) o[c] = 0.f;
+        for (int c = d; c < dpad; ++c) o[c] = 0.f;
         if (nrm) nrm[row] = (float)n2;
         a_up = __double2float_ru(sqrt(n2) * (1.0 + 1e-12));
         anorm[row] = a_up;
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(128)
                 nt2 += hv * hv;
                 if (c < 16) nh2 += hv * hv;
                 const __half st = is_ref ? __float2half(-2.0f * __half2float(hb)) : hb;   // x2 exact
-                xb[tc_elem_index(row, c)] = __half_as_ushort(st);
+                s_xb[tc_tile_index(tid, c)] = __half_as_ushort(st);
             }
             delta_up = in_range ? __double2float_ru(sqrt(dl2) * (1.0 + 1e-12)) : __int_as_float(0x7f800000);
             atilde_up = __double2float_ru(sqrt(nt2) * (1.0 + 1e-12));
@@ -180,22 +207,36 @@ __global__ void __launch_bounds__(128)
                 const __half m = __double2half(r1);
                 const double r2 = r1 - (double)__half2float(m);
                 const __half l = __double2half(r2);
-                xb[tc_elem_index(row, d)] = __half_as_ushort(h);
-                xb[tc_elem_index(row, d + 1)] = __half_as_ushort(m);
-                xb[tc_elem_index(row, d + 2)] = __half_as_ushort(l);
+                s_xb[tc_tile_index(tid, d)] = __half_as_ushort(h);
+                s_xb[tc_tile_index(tid, d + 1)] = __half_as_ushort(m);
+                s_xb[tc_tile_index(tid, d + 2)] = __half_as_ushort(l);
             } else {
                 const uint16_t one = __half_as_ushort(__float2half(1.0f));
-                xb[tc_elem_index(row, d)] = one;
-                xb[tc_elem_index(row, d + 1)] = one;
-                xb[tc_elem_index(row, d + 2)] = one;
+                s_xb[tc_tile_index(tid, d)] = one;
+                s_xb[tc_tile_index(tid, d + 1)] = one;
+                s_xb[tc_tile_index(tid, d + 2)] = one;
             }
-            for (int c = d + 3; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
+            for (int c = d + 3; c < kTcKPad; ++c) s_xb[tc_tile_index(tid, c)] = 0;
         }
     } else if (row < n_pad && xb) {
         // padding rows of the tensor-core operand: references get a norm above every real score
         // (real scores stay below 3 * kTcScaledNormMax^2 = 49152) so they never win
-        for (int c = 0; c < kTcKPad; ++c) xb[tc_elem_index(row, c)] = 0;
-        if (is_ref) xb[tc_elem_index(row, d)] = __half_as_ushort(__float2half(60000.0f));
+        for (int c = 0; c < kTcKPad; ++c) s_xb[tc_tile_index(tid, c)] = 0;
+        if (is_ref) s_xb[tc_tile_index(tid, d)] = __half_as_ushort(__float2half(60000.0f));
+    }
+    __syncthreads();
+    if (xs) {   // rows row0 .. row0 + nrows of the SIMT operand are one contiguous range
+        const int total = nrows * dpad;
+        float *dst = xs + row0 * dpad;
+        for (int i = tid; i < total; i += kPackRows) {
+            const int r = i / dpad, c = i - r * dpad;
+            dst[i] = s_xs[r * xs_stride + c];
+        }
+    }
+    if (xb && row0 < n_pad) {   // the whole 8 KB tile (n_pad is a multiple of 128)
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(s_xb);
+        uint4 *dst4 = reinterpret_cast<uint4 *>(xb + (size_t)blockIdx.x * 4096);
+        for (int i = tid; i < 512; i += kPackRows) dst4[i] = src4[i];
     }
     if (is_ref) {
         // max over the fitted set (bit patterns of non-negative floats order like unsigned ints)
@@ -216,11 +257,14 @@ int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref,
     int64_t n_pad = is_ref ? p.n_ref_pad : p.n_q_pad;
     if (!tc) n_pad = n;
     const int64_t rows = n_pad > n ? n_pad : n;
-    const int blocks = (int)((rows + 127) / 128);
+    const int blocks = (int)((rows + kPackRows - 1) / kPackRows);
+    const size_t smem = (size_t)kPackRows * d * 4 + (size_t)kPackRows * (p.dpad + 1) * 4 + 8192;
+    if (smem > 48 * 1024)
+        MEPOL_CUDA_CHECK(cudaFuncSetAttribute(pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // fp32 operands are produced in both modes (SIMT search / rescue pass); query rows that alias
     // the fitted matrix reuse the reference rows
     float *xs = is_ref ? p.rs : (p.q_is_ref ? nullptr : p.qs);
-    pack_rows_kernel<<<blocks, 128, 0, st>>>(
+    pack_rows_kernel<<<blocks, kPackRows, smem, st>>>(
         x, n, n_pad, d, p.dpad, p.mean, xs, is_ref ? p.r_nrm : nullptr,
         is_ref ? p.r_anorm : p.q_anorm, tc ? (is_ref ? p.rb : p.qb) : nullptr,
         tc ? (is_ref ? nullptr : p.q_delta) : nullptr, tc ? (is_ref ? nullptr : p.q_ahalf) : nullptr, p.glob,

@@ -25,8 +25,13 @@ __device__ __forceinline__ double exact_d2(const float *__restrict__ a, const fl
     return s;
 }
 
-// One warp per query row.  Candidates of all splits are gathered into shared memory, their exact
-// distances computed lane-parallel, then each candidate's rank is counted; ranks < k1 are output.
+// Eight lanes per query row (four rows per warp): a row carries ~6 candidates after pruning, so a whole
+// warp per row left 26 lanes idle behind six serial 29-term fma chains (786 us at N = 1M in round 1).
+// Candidates of all splits are gathered into shared memory, their exact distances computed one candidate
+// per lane (the same sequential fma chain as every other path: distances are bit-identical across
+// kernels), then each candidate's rank is counted; ranks < k1 are output.
+constexpr int kRerankSub = 8;                               // lanes per row
+constexpr int kRerankRowsPerWarp = 32 / kRerankSub;
 __global__ void __launch_bounds__(kRerankWarps * 32)
     knn_rerank_kernel(const float *__restrict__ ref, const float *__restrict__ q, int n_q, int d, int k1,
                       int cap, int n_split, const int32_t *__restrict__ cand,
@@ -35,29 +40,35 @@ __global__ void __launch_bounds__(kRerankWarps * 32)
                       double *__restrict__ rk_out, int max_cand) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *sd = reinterpret_cast<double *>(smem_raw) + (size_t)warp * max_cand;
-    int *si = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)kRerankWarps * max_cand) +
-              (size_t)warp * max_cand;
-    const int row = blockIdx.x * kRerankWarps + warp;
-    if (row >= n_q) return;
-    if (flag[row]) return;  // the exact fallback owns this row
+    const int sub = lane / kRerankSub, sl = lane % kRerankSub;
+    const int slot_in_block = warp * kRerankRowsPerWarp + sub;
+    constexpr int kRowsPerBlock = kRerankWarps * kRerankRowsPerWarp;
+    double *sd = reinterpret_cast<double *>(smem_raw) + (size_t)slot_in_block * max_cand;
+    int *si = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)kRowsPerBlock * max_cand) +
+              (size_t)slot_in_block * max_cand;
+    const int row = blockIdx.x * kRowsPerBlock + slot_in_block;
+    const bool active = row < n_q && !flag[row];            // flagged rows belong to the exact fallback
     // gather candidate indices (splits are disjoint reference ranges -> no duplicates)
     int total = 0;
-    for (int s = 0; s < n_split; ++s) {
-        const size_t slot = (size_t)row * n_split + s;
-        const int c = cand_cnt[slot];
-        for (int e = lane; e < c; e += 32) si[total + e] = cand[slot * cap + e];
-        total += c;
-    }
-    if (total < k1) {  // cannot happen for finite inputs; stay safe
-        if (lane == 0) flag[row] = 1;
-        return;
+    if (active) {
+        for (int s = 0; s < n_split; ++s) {
+            const size_t slot = (size_t)row * n_split + s;
+            const int c = cand_cnt[slot];
+            for (int e = sl; e < c; e += kRerankSub) si[total + e] = cand[slot * cap + e];
+            total += c;
+        }
+        if (total < k1) {  // cannot happen for finite inputs; stay safe
+            if (sl == 0) flag[row] = 1;
+            total = 0;
+        }
     }
     __syncwarp();
-    const float *qr = q + (size_t)row * d;
-    for (int e = lane; e < total; e += 32) sd[e] = exact_d2(qr, ref + (size_t)si[e] * d, d);
+    if (total > 0) {
+        const float *qr = q + (size_t)row * d;
+        for (int e = sl; e < total; e += kRerankSub) sd[e] = exact_d2(qr, ref + (size_t)si[e] * d, d);
+    }
     __syncwarp();
-    for (int e = lane; e < total; e += 32) {
+    for (int e = sl; e < total; e += kRerankSub) {
         const double de = sd[e];
         const int ie = si[e];
         int rank = 0;
@@ -74,10 +85,11 @@ __global__ void __launch_bounds__(kRerankWarps * 32)
 int launch_rerank(const float *ref, const float *q, const KnnPlan &p, int32_t *idx_out, double *dist_out,
                   double *rk_out, cudaStream_t st) {
     const int max_cand = p.cap * p.n_split;
-    const size_t smem = (size_t)kRerankWarps * max_cand * (sizeof(double) + sizeof(int));
+    const int rows_per_block = kRerankWarps * kRerankRowsPerWarp;
+    const size_t smem = (size_t)rows_per_block * max_cand * (sizeof(double) + sizeof(int));
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem));
-    const int blocks = (int)((p.n_q + kRerankWarps - 1) / kRerankWarps);
+    const int blocks = (int)((p.n_q + rows_per_block - 1) / rows_per_block);
     knn_rerank_kernel<<<blocks, kRerankWarps * 32, smem, st>>>(ref, q, (int)p.n_q, p.d, p.k1, p.cap,
                                                                p.n_split, p.cand, p.cand_cnt, p.flag,
                                                                idx_out, dist_out, rk_out, max_cand);
