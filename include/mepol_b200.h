@@ -30,7 +30,7 @@ extern "C" {
 
 #define MEPOL_KNN_AUTO 0 /* grid search for d <= 3, tensor-core pruner for 4 <= d <= 29 and k1 <= 12, else SIMT */
 #define MEPOL_KNN_SIMT 1 /* fp32 SIMT pruner + fp64 re-rank (any d <= 64, k1 <= 60) */
-#define MEPOL_KNN_TC 2   /* tcgen05 fp16 pruner + fp64 re-rank (d <= 29, k1 <= 12) */
+#define MEPOL_KNN_TC 2   /* tcgen05 fp16 pruner (N=256 MMAs, fp16 accumulators) + fp64 re-rank (d <= 29, k1 <= 12) */
 #define MEPOL_KNN_GRID 3 /* uniform-grid exact search in fp64 (d <= 3, k1 <= 60): the kd-tree regime */
 
 #define MEPOL_MAX_DIM 64
@@ -45,7 +45,8 @@ int mepol_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* Optional measurement hook used by bench.py: when enabled, every mepol_knn_search_f32 call records
  * a CUDA-event pair around its pruning kernel (the dominant kernel of the path) on the caller's
  * stream, up to 64 launches; mepol_profile_read waits for them and returns the per-launch
- * milliseconds.  No effect on results. */
+ * milliseconds.  No effect on results.  BENCH-ONLY: the event table is process-global and not thread-safe --
+ * call it from one thread, around searches issued from that thread. */
 int mepol_profile_enable(int on);
 int mepol_profile_read(float *ms_out, int max_n, int *n_out);
 
@@ -64,7 +65,7 @@ int mepol_profile_read(float *ms_out, int max_n, int *n_out);
  * rk_out   [n_q] float64, optional (may be NULL) -- dist_out[:, k1-1] as a contiguous column, the
  *       only distance the objective consumes (mepol.py:150).
  * stats    optional DEVICE int64[MEPOL_KNN_NSTATS]: {candidates re-ranked, rows sent to the exact
- *       fallback, buffer compactions, rows whose bf16 band overflowed in the tensor-core pruner, 0...}.
+ *       fallback, buffer compactions, rows whose fp16 band overflowed in the tensor-core pruner, 0...}.
  * Results are exact: candidates are pruned with a proven error band and re-ranked in float64;
  * rows whose candidate buffer overflows are recomputed by an exact float64 brute-force kernel.
  */
