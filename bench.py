@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--traj-len", type=int, default=500)
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep"] + sorted(CONFIG_WORKLOADS),
+                    help="sweep = BASELINE.json configs[4] (the metric's configuration, --n/--d/--k apply); the others are "
+                         "the reference's shipped configurations (configs[0..3]) as synthetic batches of their shapes")
+    ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -55,16 +59,41 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(n, d, k, traj_len):
+# BASELINE.json configs[0..3] as synthetic batches (rollouts need gym / MuJoCo):
+#   name -> (num_traj T, traj_len L, ns = particle dimension, k, particle generator)
+CONFIG_WORKLOADS = {
+    "grid_world": (20, 1200, 2, 50, "uniform6"),        # scripts/tae/grid_world.sh (k = 50 per the script)
+    "grid_world_k4": (20, 1200, 2, 4, "uniform6"),      # BASELINE.json's k = 4 reading of the same config
+    "mountain_car": (20, 400, 2, 4, "mountaincar"),     # scripts/tae/mountain_car.sh
+    "ant": (20, 500, 7, 4, "normal"),                   # scripts/tae/ant.sh, state_filter = range(7)
+    "ant_29d": (20, 500, 29, 4, "normal"),              # BASELINE.json's "29-dim" reading
+    "humanoid": (20, 500, 24, 4, "normal"),             # scripts/tae/humanoid.sh, ns = 24
+}
+
+
+def apply_workload(args):
+    if args.workload != "sweep":
+        T, L, ns, k, _ = CONFIG_WORKLOADS[args.workload]
+        args.n, args.d, args.k, args.traj_len = T * L, ns, k, L
+
+
+def workload_name(n, d, k, traj_len, workload="sweep"):
     """ONE string for both arms (the driver compares the two lines' config)."""
+    if workload != "sweep":
+        return f"{workload}: synthetic batch of the shipped configuration's shape N={n} ns={d} k={k} L={traj_len}"
     return f"synthetic sweep N={n} d={d} k={k} L={traj_len} (BASELINE.json configs[4])"
 
 
-def synth(n, d, traj_len, seed=0):
+def synth(n, d, traj_len, seed=0, kind="normal"):
     """Synthetic batch of BASELINE.md section 4: N(0,1) float32 particles (tie-free), trajectories of
-    length traj_len (last one shorter), lb = 0, lt ~ N(0, 0.01^2)."""
+    length traj_len (last one shorter), lb = 0, lt ~ N(0, 0.01^2).  kind: the particle generator of the
+    shipped configurations (GridWorld uniform in [-6,6]^2, MountainCar x in [-1.2,0.6], v in [-0.07,0.07])."""
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((n, d), dtype=np.float32)
+    if kind == "uniform6":
+        x = rng.uniform(-6.0, 6.0, (n, d)).astype(np.float32)
+    elif kind == "mountaincar":
+        x = np.stack([rng.uniform(-1.2, 0.6, n), rng.uniform(-0.07, 0.07, n)], 1).astype(np.float32)
     lt = rng.normal(0.0, 0.01, n).astype(np.float32)
     lb = np.zeros(n, dtype=np.float32)
     lens = [traj_len] * (n // traj_len)
@@ -303,7 +332,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores, pools = host_threads()
-    x, lt, lb, lens = synth(args.n, args.d, args.traj_len)
+    kind = CONFIG_WORKLOADS[args.workload][4] if args.workload != "sweep" else "normal"
+    x, lt, lb, lens = synth(args.n, args.d, args.traj_len, args.seed, kind)
     ref = CpuReference(x, lt, lb, lens, args.k, args.traj_len)
     rows = cpu_sample_rows(x, args.k, max(2.0, args.cpu_seconds / 2))
     warm = min(args.warmup, 1)
@@ -319,7 +349,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args.n, args.d, args.k, args.traj_len)},
+            "config": {"workload": workload_name(args.n, args.d, args.k, args.traj_len, args.workload), "seed": args.seed},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": ref.kind,
                              "sample": ref.describe(rows, ts, ti, cores), "threadpools": pools,
                              "versions": ref.versions(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
@@ -376,7 +406,8 @@ def run_ours(args):
     if n % world:
         n -= n % world
     algo = {"auto": _lib.KNN_AUTO, "simt": _lib.KNN_SIMT, "tc": _lib.KNN_TC}[args.algo]
-    x, lt, lb, lens = synth(n, d, args.traj_len)
+    kind = CONFIG_WORKLOADS[args.workload][4] if args.workload != "sweep" else "normal"
+    x, lt, lb, lens = synth(n, d, args.traj_len, args.seed, kind)
     G, B = constants(d, k)
     lo, hi = shard_bounds(n, world, rank)
     n_traj = len(lens)
@@ -607,6 +638,16 @@ def run_ours(args):
                 "peak_burst": peaks["tflops_burst"],
                 "frac_of_burst": (achieved / peaks["tflops_burst"]) if achieved else None,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}): the kernel is timed inside a long step"}
+    if kernel == "knn_grid_search_kernel":
+        # d <= 3 (the reference's kd-tree regime): O(N k) uniform-grid search, bounded by memory not by the tensor pipe
+        gbytes = float((hi - lo) * (4 * d + 16 + k1 * 12 + 8))
+        gbs = gbytes / (prune_avg * 1e-3) / 1e9 if prune_ms else None
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": (gbs / peaks["hbm"]) if gbs else None, "traffic": None, "kernel": kernel, "kernel_ms": prune_avg,
+                    "launches_timed": len(prune_ms), "algorithmic_bytes_per_launch": gbytes,
+                    "note": "particles in + 16 B grid point + (k+1) x (int32 index + float64 distance) + r_k out per query row; "
+                            "latency-bound ring walk, the figure is a lower bound of the traffic",
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['src']})"}
     comp["iw_roofline"] = None
     if "iw_kernels_fwd_ms" in comp:
         bytes_iw = (36 + 20 * k) * n
@@ -643,7 +684,7 @@ def run_ours(args):
             "warmup": warmup_done, "warmup_requested": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if algo == _lib.KNN_SIMT else "f16",
             "data": "synthetic",
-            "config": {"workload": workload_name(n, d, k, args.traj_len),
+            "config": {"workload": workload_name(n, d, k, args.traj_len, args.workload), "seed": args.seed,
                        "algo": args.algo, "parallelism": f"query rows sharded x{world}, refs all-gathered (NCCL)",
                        "l2": "inputs larger than L2: packed refs + candidates > 126 MB per step, no flush needed"},
             "clocks": clocks, "e2e": e2e,
@@ -657,6 +698,7 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    apply_workload(a)
     if a.impl == "reference":
         run_reference(a)
     else:

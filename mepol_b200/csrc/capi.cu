@@ -126,10 +126,21 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
             const int64_t nrb = p.n_q_pad / 256, tiles = p.n_ref_pad / 128;
             const int64_t rounds = nrb / sms, tail = nrb - rounds * sms;
             p.tc_tail_split = 1;
-            if (rounds >= 1 && rounds <= 12 && tail > 0 && tiles >= 512) {
-                int64_t s_ = sms / tail;
-                if (s_ > 4) s_ = 4;
-                if (s_ >= 2) p.tc_tail_split = (int)s_;
+            if (rounds <= 12 && tail > 0 && tiles >= 256) {
+                // The tail takes ceil(tail * s / sms) rounds of 1/s length: pick the split (<= 4 ranges of >= 256
+                // tiles each) that makes it shortest, the smallest such split on a draw.  Shorter ranges lose
+                // more to their own warm-up and append ramp than the balance wins (N = 64k: 108 tail blocks cut
+                // in 4 would finish in 0.75 of a round but measured 0.72 vs 0.62 ms, profiles/r02_tc2_notes.md).
+                int64_t max_s = tiles / 256 < 4 ? tiles / 256 : 4;
+                if (const char *ms = getenv("MEPOL_TC_MAX_TAIL_SPLIT")) max_s = atoi(ms);   // tuning aid; every value is exact
+                double best = 1e30;
+                for (int64_t s_ = 1; s_ <= max_s; ++s_) {
+                    const double len = (double)((tail * s_ + sms - 1) / sms) / (double)s_;
+                    if (len < best - 1e-9) {
+                        best = len;
+                        p.tc_tail_split = (int)s_;
+                    }
+                }
             }
             p.n_split = p.tc_tail_split;
         }

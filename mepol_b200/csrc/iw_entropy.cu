@@ -552,8 +552,8 @@ __global__ void csr_fill_kernel(const int32_t *__restrict__ idx, int n, int k1, 
 // order (and therefore its bits) reproducible run to run.  The in-degree of a particle is NOT bounded
 // by k: with exact duplicates (MountainCar's wall states) every copy lists the same k lowest-index
 // copies, so a few hub rows collect thousands of entries.  Rows of up to kCsrShortRow entries are
-// insertion-sorted by one thread; longer ones are queued for csr_sort_long_rows_kernel.
-constexpr int kCsrShortRow = 32;
+// insertion-sorted by one thread (<= ~16k steps); longer ones are queued for csr_sort_long_rows_kernel.
+constexpr int kCsrShortRow = 256;   // k = 50 (GridWorld) makes ~50-100-entry rows the norm: still one thread's job
 __global__ void csr_sort_rows_kernel(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ col,
                                      int32_t *__restrict__ long_list, int32_t *__restrict__ long_count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
