@@ -159,6 +159,26 @@ int mepol_iw_entropy_fwd_bwd_f64(const double *logp_t, const double *logp_b, con
                                  double *scal, double *grad_unit, void *workspace,
                                  size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diagonal-Gaussian log-probability of the policy head.  Replaces the elementwise tail of
+ * GaussianPolicy.get_log_p (src/policy.py:43-51):
+ *     log p = sum_j -0.5 * (log(2 pi) + 2 log_std_j + (a_j - mean_j)^2 / (exp(log_std_j) + 1e-7)^2)
+ * mean [n, A] is the MLP output (policy.py:54, computed by the caller), actions [n, A], log_std [A] (all device,
+ * row-major), logp [n].  The backward takes d loss / d logp [n] and writes d / d mean [n, A] and d / d log_std [A]
+ * (reduced over the n states in a fixed order).  A <= 64.
+ */
+int mepol_gauss_logp_workspace_bytes(int64_t n, int A, size_t *bytes);
+int mepol_gauss_logp_fwd_f32(const float *mean, const float *actions, const float *log_std, int64_t n, int A,
+                             float *logp, void *stream);
+int mepol_gauss_logp_fwd_f64(const double *mean, const double *actions, const double *log_std, int64_t n,
+                             int A, double *logp, void *stream);
+int mepol_gauss_logp_bwd_f32(const float *mean, const float *actions, const float *log_std,
+                             const float *g_logp, int64_t n, int A, float *g_mean, float *g_log_std,
+                             void *workspace, size_t workspace_bytes, void *stream);
+int mepol_gauss_logp_bwd_f64(const double *mean, const double *actions, const double *log_std,
+                             const double *g_logp, int64_t n, int A, double *g_mean, double *g_log_std,
+                             void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,11 @@ SIGNATURES = {
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mepol_iw_entropy_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mepol_iw_entropy_bwd_f64": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mepol_gauss_logp_workspace_bytes": (_i32, [_i64, _i32, _c.POINTER(_sz)]),
+    "mepol_gauss_logp_fwd_f32": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mepol_gauss_logp_fwd_f64": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mepol_gauss_logp_bwd_f32": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "mepol_gauss_logp_bwd_f64": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -88,6 +93,12 @@ def rev_csr_workspace_bytes(n, k):
 def iw_workspace_bytes(n, n_traj):
     out = _sz(0)
     check(load().mepol_iw_workspace_bytes(n, n_traj, ctypes.byref(out)), "mepol_iw_workspace_bytes")
+    return out.value
+
+
+def gauss_logp_workspace_bytes(n, A):
+    out = _sz(0)
+    check(load().mepol_gauss_logp_workspace_bytes(n, A, ctypes.byref(out)), "mepol_gauss_logp_workspace_bytes")
     return out.value
 
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmepol_b200.so")
-SOURCES = ["capi.cu", "knn_prep.cu", "knn_simt.cu", "knn_tc.cu", "knn_tc2.cu", "knn_grid.cu", "knn_rerank.cu", "iw_entropy.cu"]
+SOURCES = ["capi.cu", "knn_prep.cu", "knn_simt.cu", "knn_tc.cu", "knn_tc2.cu", "knn_grid.cu", "knn_rerank.cu", "iw_entropy.cu", "gauss_logp.cu"]
 NVCC = os.environ.get("MEPOL_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

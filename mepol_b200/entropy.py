@@ -210,9 +210,52 @@ def mirror_params(policy, device, dtype, requires_grad):
     return out
 
 
+class GaussLogPFunction(torch.autograd.Function):
+    """log p(a | s) of the diagonal-Gaussian head from the MLP mean: the elementwise tail of
+    GaussianPolicy.get_log_p (policy.py:43-51) as ONE kernel forward and one backward
+    (mepol_gauss_logp_{fwd,bwd}_{f32,f64}) instead of ~20 ATen elementwise launches on [n, A] temporaries."""
+
+    @staticmethod
+    def forward(ctx, mean, actions, log_std):
+        if not mean.is_cuda:
+            raise _lib.MepolError("GaussLogPFunction needs CUDA tensors (there is no CPU fallback)")
+        dt = mean.dtype
+        if dt not in (torch.float32, torch.float64):
+            raise ValueError("the policy head must be float32 or float64")
+        mean_c, act_c, ls_c = mean.detach().contiguous(), actions.detach().to(dt).contiguous(), log_std.detach().to(dt).contiguous()
+        n, A = mean_c.shape
+        out = torch.empty(n, dtype=dt, device=mean.device)
+        suffix = "f32" if dt == torch.float32 else "f64"
+        with _on(mean.device):
+            rc = getattr(_lib.load(), "mepol_gauss_logp_fwd_" + suffix)(
+                mean_c.data_ptr(), act_c.data_ptr(), ls_c.data_ptr(), n, A, out.data_ptr(), _stream_ptr(mean.device))
+        _lib.check(rc, "mepol_gauss_logp_fwd_" + suffix)
+        ctx.save_for_backward(mean_c, act_c, ls_c)
+        ctx.suffix = suffix
+        return out
+
+    @staticmethod
+    def backward(ctx, g_logp):
+        mean_c, act_c, ls_c = ctx.saved_tensors
+        n, A = mean_c.shape
+        dev, dt = mean_c.device, mean_c.dtype
+        g = g_logp.detach().to(dt).contiguous()
+        g_mean = torch.empty_like(mean_c)
+        g_ls = torch.empty(A, dtype=dt, device=dev)
+        ws = torch.empty(_lib.gauss_logp_workspace_bytes(n, A), dtype=torch.uint8, device=dev)
+        with _on(dev):
+            rc = getattr(_lib.load(), "mepol_gauss_logp_bwd_" + ctx.suffix)(
+                mean_c.data_ptr(), act_c.data_ptr(), ls_c.data_ptr(), g.data_ptr(), n, A, g_mean.data_ptr(),
+                g_ls.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        _lib.check(rc, "mepol_gauss_logp_bwd_" + ctx.suffix)
+        return g_mean, None, g_ls
+
+
 def gaussian_log_p(policy, params, states, actions):
     """policy.py:43-61 on device tensors with mirrored parameters `params` (ordered like
-    policy.parameters(): log_std first, then net.*, then mean.*)."""
+    policy.parameters(): log_std first, then net.*, then mean.*).  The MLP runs in torch (cuBLAS); on CUDA
+    tensors the log-prob tail is the hand-written kernel pair behind GaussLogPFunction.  (CPU tensors --
+    only the host-logic test of the parameter ordering uses them -- take the literal expression.)"""
     names = [n for n, _ in policy.named_parameters()]
     table = dict(zip(names, params))
     h = states
@@ -223,6 +266,8 @@ def gaussian_log_p(policy, params, states, actions):
             h = m(h)
     mean = torch.nn.functional.linear(h, table["mean.weight"], table["mean.bias"])
     log_std = table["log_std"]
+    if mean.is_cuda:
+        return GaussLogPFunction.apply(mean, actions, log_std)
     return torch.sum(-0.5 * (_LOG_2PI + 2.0 * log_std
                              + (actions - mean) ** 2 / (torch.exp(log_std) + POLICY_EPS) ** 2), dim=1)
 

@@ -333,3 +333,33 @@ def test_cuda_graph_replay_equals_eager_launches_over_several_steps():
     for a, b in zip(runs[True][1], runs[False][1]):
         assert torch.equal(a, b)
     assert torch.equal(runs[True][2], runs[False][2])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("n,A", [(10000, 8), (777, 1), (24000, 2), (5000, 17)])
+def test_gauss_logp_kernels_match_the_reference_expression(n, A, dtype, tol):
+    """mepol_gauss_logp_{fwd,bwd} against autograd of the literal expression of policy.py:43-51
+    (float64 on the CPU): value, d/d mean and d/d log_std (a reduction over all states)."""
+    g = torch.Generator().manual_seed(n + A)
+    mean = torch.randn((n, A), generator=g, dtype=torch.float64)
+    act = 0.6 * torch.randn((n, A), generator=g, dtype=torch.float64)
+    ls = -0.5 + 0.3 * torch.randn(A, generator=g, dtype=torch.float64)
+    up = torch.randn(n, generator=g, dtype=torch.float64)
+    m_ref, ls_ref = mean.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    ref = torch.sum(-0.5 * (math.log(2 * math.pi) + 2 * ls_ref + (act - m_ref) ** 2 / (torch.exp(ls_ref) + 1e-7) ** 2), dim=1)
+    ref.backward(up)
+    m_dev = mean.to("cuda", dtype).requires_grad_(True)
+    ls_dev = ls.to("cuda", dtype).requires_grad_(True)
+    out = E.GaussLogPFunction.apply(m_dev, act.to("cuda", dtype), ls_dev)
+    out.backward(up.to("cuda", dtype))
+    sc = ref.detach().abs().max().item()
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= tol * sc
+    sc = m_ref.grad.abs().max().item()
+    assert (m_dev.grad.cpu().double() - m_ref.grad).abs().max().item() <= tol * sc
+    sc = ls_ref.grad.abs().max().item()
+    assert (ls_dev.grad.cpu().double() - ls_ref.grad).abs().max().item() <= 10 * tol * sc
+    # deterministic: the log_std reduction folds block partials in a fixed order
+    m2 = mean.to("cuda", dtype).requires_grad_(True)
+    ls2 = ls.to("cuda", dtype).requires_grad_(True)
+    E.GaussLogPFunction.apply(m2, act.to("cuda", dtype), ls2).backward(up.to("cuda", dtype))
+    assert torch.equal(ls2.grad, ls_dev.grad) and torch.equal(m2.grad, m_dev.grad)
