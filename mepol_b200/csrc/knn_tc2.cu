@@ -418,9 +418,17 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             const float band0 = live ? tc_band(q_anorm[row], q_delta[row], A, D) * 1.001f + bandk * c_first +
                                            2.01f * acc_scale * kT2Align * 2.0f * m_add + 1e-5f
                                      : 0.f;
-            uint32_t tau2 = h2_splat_up(tau);
             int cnt = 0;
             bool ovf = false;
+            // fp16 RANGE of the accumulator: every partial sum of a score is bounded by 2 ||x~|| max||y~|| + A^2.
+            // Rows of the fitted set satisfy it by construction (norms <= 128 -> < 49152); a foreign query with a
+            // large norm could drive a partial sum to +-inf and hide a true neighbour behind +inf.  Such rows
+            // collect nothing and go to the exact fallback (like rows whose operand does not fit fp16 at all).
+            if (live && !(2.0f * a_row * AtildeMax + 1.001f * A * A < 60000.0f)) {
+                ovf = true;
+                tau = -INF;
+            }
+            uint32_t tau2 = h2_splat_up(tau);
 #pragma unroll
             for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
             const int rot = kDump ? 0 : (rblk * (256 / NC)) % tiles;

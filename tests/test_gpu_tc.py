@@ -261,3 +261,21 @@ def test_band_holds_on_adversarial_data(kind, variant, monkeypatch):
         assert torch.equal(a.indices, b.indices)
     else:
         assert torch.equal(a.indices, b.indices)
+
+
+@pytest.mark.parametrize("factor", [3.0, 20.0, 60.0, 400.0])
+@pytest.mark.parametrize("variant", ["3", "2"])
+def test_foreign_queries_with_large_norms_stay_exact(factor, variant, monkeypatch):
+    """Queries that are NOT rows of the fitted set may have norms far beyond its extent while every
+    component still fits fp16.  With fp16 accumulators a partial sum of such a row could overflow to
+    +-inf; those rows must be detected (|partial| <= 2 ||x~|| max||y~|| + A^2 >= fp16 range) and served by
+    the exact fallback, the others pruned as usual -- results equal the oracle either way."""
+    from oracle import knn_oracle
+    rng = np.random.default_rng(int(factor))
+    x = rng.standard_normal((8000, 29)).astype(np.float32)
+    q = (rng.standard_normal((700, 29)) * factor).astype(np.float32)
+    q[:50] = x[:50]                                       # some ordinary rows in the same batch
+    monkeypatch.setenv("MEPOL_TC_VARIANT", variant)
+    res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), 5, queries=torch.from_numpy(q).cuda(), algo=_lib.KNN_TC)
+    ref_d, ref_i = knn_oracle.knn_c(x, 5, queries=q, mode="kd_tree")
+    assert_knn_matches(res.distances.cpu().numpy(), res.indices.cpu().numpy(), ref_d, ref_i, x, queries=q, rtol=1e-12)
