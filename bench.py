@@ -423,7 +423,14 @@ def run_ours(args):
     searcher = ShardedSearch(n, d, k1, dev, algo=algo)
     # sklearn's output arrays on the host (indices int64, distances float64): one page-locked shared-memory
     # block that every rank's GPU writes its own rows into (G concurrent PCIe transfers)
-    host_results = None if args.no_e2e else SharedHostResults(n, k1, device=dev)
+    host_results, host_results_note = None, None
+    if not args.no_e2e:
+        try:
+            host_results = SharedHostResults(n, k1, device=dev)
+        except Exception as e:          # e.g. a tiny /dev/shm: fall back to gathering on rank 0's GPU (the slower path)
+            host_results_note = f"shared host block unavailable ({e!r}); results gathered on rank 0's GPU instead"
+            fb_idx = torch.empty((n, k1), dtype=torch.int64).pin_memory() if rank == 0 else None
+            fb_dist = torch.empty((n, k1), dtype=torch.float64).pin_memory() if rank == 0 else None
     grad_host = torch.empty((n,), dtype=torch.float32).pin_memory() if rank == 0 else None
     scal_host = torch.empty((2,), dtype=torch.float64).pin_memory() if rank == 0 else None
     copy_stream = torch.cuda.Stream(device=dev)
@@ -444,14 +451,18 @@ def run_ours(args):
 
     def step_e2e():
         sh = x_pin.to(dev, non_blocking=True)                                   # H2D particles (own shard)
-        idx_full, rk_full, _ = searcher(sh)
+        idx_full, rk_full, dist_full = searcher(sh, gather_distances=host_results is None)
         # every rank sends the rows it searched to the host arrays on a copy stream (D2H indices as int64 +
         # distances float64: 16 * k1 bytes per row), while rank 0 goes on with the objective
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
-            host_results.push(searcher.own_idx, searcher.own_dist)
+            if host_results is not None:
+                host_results.push(searcher.own_idx, searcher.own_dist)
+            elif rank == 0:
+                fb_idx.copy_(idx_full, non_blocking=True)
+                fb_dist.copy_(dist_full, non_blocking=True)
         if rank == 0:
             ltt = lt_pin.to(dev, non_blocking=True).requires_grad_(True)         # H2D log-probs
             lbt = lb_pin.to(dev, non_blocking=True)
@@ -687,7 +698,7 @@ def run_ours(args):
             "config": {"workload": workload_name(n, d, k, args.traj_len, args.workload), "seed": args.seed,
                        "algo": args.algo, "parallelism": f"query rows sharded x{world}, refs all-gathered (NCCL)",
                        "l2": "inputs larger than L2: packed refs + candidates > 126 MB per step, no flush needed"},
-            "clocks": clocks, "e2e": e2e,
+            "clocks": clocks, "e2e": (dict(e2e, note=host_results_note) if (e2e and host_results_note) else e2e),
             "gpu_launches": (launches * args.steps) if launches else None,
             "gpu_launches_per_step": launch_names if launches else {"uncounted": launch_names},
             "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "components": comp}

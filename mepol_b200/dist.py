@@ -136,27 +136,37 @@ class SharedHostResults:
         self.device = device
         self.lo, self.hi = shard_bounds(n, self.world, self.rank)
         nbytes = 16 * n * k1
-        name = [None]
-        if self.rank == 0:
-            name[0] = f"/dev/shm/mepol_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}"
-            with open(name[0], "wb") as f:
-                f.truncate(nbytes)
-        if self.world > 1:
-            dist.broadcast_object_list(name, src=0, group=group)
-        self._path = name[0]
-        self._file = open(self._path, "r+b")
-        self._map = mmap.mmap(self._file.fileno(), nbytes)
-        if self.world > 1:
-            dist.barrier(group=group)
-        if self.rank == 0:
-            os.unlink(self._path)               # the mapping keeps the memory alive; nothing is left behind
-        buf = torch.frombuffer(self._map, dtype=torch.uint8)
         self._registered = False
-        if device is not None and torch.device(device).type == "cuda":
-            rc = torch.cuda.cudart().cudaHostRegister(buf.data_ptr(), nbytes, 0)
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister of the shared result block failed (rc={int(rc)})")
-            self._registered = True
+        self._map = self._file = None
+        if self.world == 1:
+            # one rank: a plain page-locked block does it (no shared mapping needed)
+            pin = device is not None and torch.device(device).type == "cuda"
+            buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+        else:
+            name = [None]
+            if self.rank == 0:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < nbytes + (8 << 20):
+                    name[0] = ""                 # every rank must learn about the failure (no hang)
+                else:
+                    name[0] = f"/dev/shm/mepol_b200_{os.getpid()}_{uuid.uuid4().hex[:12]}"
+                    with open(name[0], "wb") as f:
+                        f.truncate(nbytes)
+            dist.broadcast_object_list(name, src=0, group=group)
+            if not name[0]:
+                raise RuntimeError(f"/dev/shm has less than {nbytes >> 20} MiB free for the shared result block")
+            self._path = name[0]
+            self._file = open(self._path, "r+b")
+            self._map = mmap.mmap(self._file.fileno(), nbytes)
+            dist.barrier(group=group)
+            if self.rank == 0:
+                os.unlink(self._path)               # the mapping keeps the memory alive; nothing is left behind
+            buf = torch.frombuffer(self._map, dtype=torch.uint8)
+            if device is not None and torch.device(device).type == "cuda":
+                rc = torch.cuda.cudart().cudaHostRegister(buf.data_ptr(), nbytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister of the shared result block failed (rc={int(rc)})")
+                self._registered = True
         self._buf = buf
         self.indices = buf[:8 * n * k1].view(torch.int64).view(n, k1)
         self.distances = buf[8 * n * k1:].view(torch.float64).view(n, k1)
@@ -169,7 +179,7 @@ class SharedHostResults:
 
     def wait(self):
         """All ranks' copies have landed (stream sync + barrier)."""
-        if self._registered:
+        if self.device is not None and torch.device(self.device).type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)
@@ -180,8 +190,9 @@ class SharedHostResults:
         if self._registered:
             torch.cuda.cudart().cudaHostUnregister(self._buf.data_ptr())
         self.indices = self.distances = self._buf = None
-        try:
-            self._map.close()
-        except BufferError:
-            pass
-        self._file.close()
+        if self._map is not None:
+            try:
+                self._map.close()
+            except BufferError:
+                pass
+            self._file.close()
