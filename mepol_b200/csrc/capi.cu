@@ -118,9 +118,7 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
         p.rows_per_cta = 256;
         p.n_split = 1;
         p.cap = 32;   // kTcSoftCap of knn_tc.cu (tc_supported guarantees 2*k1 + 8 <= 32)
-        // whole B tiles: 256 references (knn_tc2.cu; knn_tc.cu takes them as 2 x 128) or 240 (knn_tc2.cu with the A
-        // operand in TMEM), packed in 128-row operand tiles
-        p.n_ref_pad = ((n_ref + 239) / 240 * 240 + 255) / 256 * 256;
+        p.n_ref_pad = (n_ref + 255) / 256 * 256;   // whole 256-reference B tiles (knn_tc2.cu); knn_tc.cu takes them as 2 x 128
         p.n_q_pad = (n_q + 255) / 256 * 256;
         {
             // Tail balancing of the persistent grid: with few rounds (multi-GPU shards), the blocks of the
@@ -292,8 +290,8 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
     if (p.algo == MEPOL_KNN_TC)
         {
             const int tv = tc_variant();
-            rc = tv == 4 ? launch_prune_tc2(p, 128, 1, false, st) : tv == 5 ? launch_prune_tc2(p, 128, 2, false, st)
-                 : (tv >= 0 && tv <= 2) ? launch_prune_tc(p, st) : launch_prune_tc2(p, 256, 1, tv == 9, st);
+            rc = tv == 4 ? launch_prune_tc2(p, 128, 1, st) : tv == 5 ? launch_prune_tc2(p, 128, 2, st)
+                 : (tv >= 0 && tv <= 2) ? launch_prune_tc(p, st) : launch_prune_tc2(p, 256, 1, st);
         }
     else
         rc = launch_prune_simt(p, st);

@@ -73,7 +73,7 @@ bool tc_supported(int d, int k1);
 int launch_prune_tc(const KnnPlan &p, cudaStream_t st);
 int launch_tc_dump(const KnnPlan &p, float *dump, cudaStream_t st);
 // knn_tc2.cu
-int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, bool ts, cudaStream_t st);
+int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st);
 int launch_tc2_dump(const KnnPlan &p, float *dump, cudaStream_t st);
 // knn_grid.cu
 bool grid_supported(int d, int k1);

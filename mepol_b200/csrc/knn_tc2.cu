@@ -45,14 +45,8 @@ constexpr int kT2Rows = 256;
 //             accumulators of the CTA are each other's second buffer (3 tcgen05 instructions per tile)
 //   NC = 128: two 128-column buffers per accumulator (the arrangement of knn_tc.cu), 6 instructions per
 //             256 x 128 scores, but the TMEM hand-shake of one buffer hides behind the other
-// kTS: the query block (the MMA's A operand, constant over a unit's whole sweep) lives in TENSOR MEMORY instead of
-//   shared memory (tcgen05.mma with a TMEM A operand).  A 128 x 256 x 16 MMA in the smem-smem form reads 12 KB of
-//   shared memory per 128 cycles (96 of the SM's 128 B/clk), a third of it the same A tile over and over; with A in
-//   TMEM the tensor pipe only streams B (64 B/clk).  A needs 16 TMEM columns per accumulator (32 fp16 = 64 B per row),
-//   which come out of the accumulator: B tiles are 240 references wide (columns 0-239 scores, 240-255 the A operand).
-template <int NC, bool kTS = false> struct T2Cfg {
-    static constexpr int kTileRefs = kTS ? NC - 16 : NC;              // references per B tile
-    static constexpr int kStageBytes = kTileRefs * kTcKPad * 2;       // 8 / 16 KB (15 KB with kTS)
+template <int NC> struct T2Cfg {
+    static constexpr int kStageBytes = NC * kTcKPad * 2;              // 8 / 16 KB
     static constexpr int kStages = NC == 256 ? 3 : 4;
     static constexpr int kBufs = 256 / NC;                            // TMEM buffers per accumulator
     static constexpr int kRegs = NC / 2;                              // packed registers per row and tile
@@ -66,7 +60,6 @@ constexpr int kT2Cap = 64;
 constexpr int kT2BufStride = kT2Cap + 1;
 constexpr int kT2EpiWarps = 8;
 constexpr int kT2Threads = (kT2EpiWarps + 4) * 32;
-constexpr int kT2TsRefs = T2Cfg<256, true>::kTileRefs;
 constexpr int kT2EpiRegs = 216;
 constexpr int kT2AuxRegs = 40;
 constexpr int kT2StgStride = 17;                     // words per lane in the per-warp staging tile
@@ -82,8 +75,8 @@ static_assert(T2Cfg<256>::kStages * T2Cfg<256>::kStageBytes <= 3 * 16384 && T2Cf
               "B ring does not fit its shared-memory slice");
 
 // fp16 accumulator (c_format 0), fp16 A/B, K-major, N = NC, M = 128
-template <int N> constexpr uint32_t t2_idesc() {
-    return (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+template <int NC> constexpr uint32_t t2_idesc() {
+    return (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // Error model of the tensor core's fp16 accumulation, per K = 16 step (measured on B200 with
 // scripts/exp_tc2.py, pinned by tests/test_gpu_tc.py; each constant is TWICE what was observed, and the
@@ -137,15 +130,6 @@ __device__ __forceinline__ void tc_ld128_packed(uint32_t taddr, uint32_t (&r)[64
         : "r"(taddr)
         : "memory");
 }
-// the thread's 32 fp16 operand values (16 registers) -> TMEM columns taddr .. taddr+15 of its lane
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 template <int kN> __device__ __forceinline__ void tc_ld_packed_at(uint32_t taddr, uint32_t *r) {
     if (kN == 128)
         tc_ld256_packed(taddr, *reinterpret_cast<uint32_t(*)[128]>(r));
@@ -162,7 +146,7 @@ template <int kN> __device__ __forceinline__ void tc_ld_packed_at(uint32_t taddr
 // kFuse = accumulator buffers an epilogue warp unloads per loop iteration (2 only with NC = 128: both
 // 128-column buffers are pulled into 128 registers back to back and filtered as ONE 256-score row, which
 // halves the per-tile fixed costs of the epilogue while the MMAs keep the finer-grained hand-shake)
-template <bool kDump, int K1, int NC, int kFuse, bool kTS>
+template <bool kDump, int K1, int NC, int kFuse>
 __global__ void __launch_bounds__(kT2Threads, 1)
     knn_prune_tc2_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
                          const float *__restrict__ q_delta, const float *__restrict__ q_ahalf, int n_q,
@@ -179,13 +163,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     constexpr int dbg = 0;
 #endif
     extern __shared__ __align__(1024) unsigned char smem[];
-    using Cfg = T2Cfg<NC, kTS>;
-    constexpr int kT2Stages = Cfg::kStages, kT2StageBytes = Cfg::kStageBytes, kT2TileRefs = Cfg::kTileRefs;
-    static_assert(!kTS || (NC == 256 && kFuse == 1), "the TMEM A operand belongs to the N = 256 arrangement");
+    using Cfg = T2Cfg<NC>;
+    constexpr int kT2Stages = Cfg::kStages, kT2StageBytes = Cfg::kStageBytes, kT2TileRefs = NC;
     constexpr int kBufs = Cfg::kBufs, kRegs = Cfg::kRegs * kFuse, kGroups = Cfg::kGroups * kFuse;
     constexpr int kSubRegs = Cfg::kRegs, kSubGroups = Cfg::kGroups;
     static_assert(kFuse == 1 || (kFuse == 2 && NC == 128), "fusing needs the two-buffer arrangement");
-    constexpr uint32_t kT2Idesc = t2_idesc<kT2TileRefs>();
+    constexpr uint32_t kT2Idesc = t2_idesc<NC>();
     const uint32_t sbase = smem_u32(smem);
     // the warp index goes through a shuffle: it tells the compiler that it is warp-uniform, so per-role
     // addresses live in uniform registers and the tcgen05 operands need no R2UR waterfall
@@ -209,8 +192,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             mbar_init(bar_done0 + 8 * s, 1);
         }
         for (int b = 0; b < 4; ++b) mbar_init(bar_acc_empty + 8 * b, kT2EpiWarps / 2);
-        mbar_init(bar_a_full, kTS ? kT2EpiWarps / 2 : 1);     // kTS: "A operand of accumulator 0 / 1 is in TMEM"
-        mbar_init(bar_a_empty, kTS ? kT2EpiWarps / 2 : 2);    //      (one arrival per epilogue warp)
+        mbar_init(bar_a_full, 1);
+        mbar_init(bar_a_empty, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kT2EpiWarps + 1) {
@@ -255,12 +238,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
                 int rblk, sp, tile0;
                 const int tiles = unit_of(u, rblk, sp, tile0);
-                if (!kTS) {
-                    mbar_wait(bar_a_empty, (rbi & 1) ^ 1);
-                    mbar_arrive_expect_tx(bar_a_full, 2 * kTcTileBytes);
-                    bulk_g2s(sbase + kT2SmemA, qb + (size_t)rblk * kT2Rows * kTcKPad, 2 * kTcTileBytes, bar_a_full);
-                }
-                const int rot = kDump ? 0 : (rblk * 256 / kT2TileRefs) % tiles;      // start at the row block's own references
+                mbar_wait(bar_a_empty, (rbi & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_a_full, 2 * kTcTileBytes);
+                bulk_g2s(sbase + kT2SmemA, qb + (size_t)rblk * kT2Rows * kTcKPad, 2 * kTcTileBytes, bar_a_full);
+                const int rot = kDump ? 0 : (rblk * (256 / NC)) % tiles;      // start at the row block's own references
                 const int sweep = tiles + warm_of(tiles);
                 for (int j = 0; j < sweep; ++j, ++it) {
                     int jt = j + rot;
@@ -286,16 +267,65 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const uint64_t b_desc_base = umma_desc(sbase + kT2SmemB, 128, 512);
         const uint32_t my_commit = t == 0 ? bar_done0 : bar_done1;
         const uint32_t d_tmem0 = tmem_base + t * 256;
-        const uint32_t a_tmem = d_tmem0 + kT2TileRefs;              // kTS: 16 columns behind the accumulator's scores
         const uint32_t my_empty0 = bar_acc_empty + 16 * t;
         uint32_t it = 0, rbi = 0;
         long long iprof[4] = {0, 0, 0, 0};
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++rbi) {
             int rblk, sp, tile0;
             const int tiles = unit_of(u, rblk, sp, tile0);
-            mbar_wait(kTS ? bar_a_full + 8 * t : bar_a_full, rbi & 1);
-            if (kTS) tc_fence_after();
+            mbar_wait(bar_a_full, rbi & 1);
             const int sweep = ((dbg & 1) && t == 1) ? 0 : tiles + warm_of(tiles);
+#ifndef MEPOL_BRINGUP
+            if (kBufs == 1) {
+                // Two waits in sequence, each on ONE address for the whole warp (a uniform-address TRYWAIT, no vote):
+                // first the stage -- normally complete long before the accumulator comes back, the producer runs two
+                // stages ahead -- which keeps it off the critical chain, then the accumulator.  Measured against one
+                // merged warp-wide wait with per-lane addresses (interleaved A/B, profiles/r02_tc2_notes.md section 7):
+                // -2.7 % at N = 1M, -3.4 % at 262k, -3.6 % at 64k.
+                auto issue_loop = [&](auto two_c) {
+                    constexpr bool kTwo = decltype(two_c)::value;
+                    uint32_t st = it % kT2Stages, fpar = (it / kT2Stages) & 1;
+                    for (int j = 0; j < sweep; ++j) {
+                        const uint64_t bd0 = b_desc_base + (uint64_t)((st * kT2StageBytes) >> 4);
+                        mbar_wait(bar_full + 8 * st, fpar);
+                        mbar_wait(my_empty0, (it & 1) ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            tc_mma_f16(d_tmem0, a_desc0, bd0, kT2Idesc, 0);
+                            if (kTwo) tc_mma_f16(d_tmem0, a_desc1, bd0 + (256 >> 4), kT2Idesc, 1);
+                            tc_commit(my_commit + 8 * st);
+                        }
+                        __syncwarp();
+                        ++it;
+                        if (++st == (uint32_t)kT2Stages) {
+                            st = 0;
+                            fpar ^= 1;
+                        }
+                    }
+                };
+#ifdef MEPOL_TC2_DBGMODES
+                if (k_steps > 2) {       // timing only: extra accumulate steps
+                    for (int j = 0; j < sweep; ++j, ++it) {
+                        const uint32_t st = it % kT2Stages;
+                        const uint64_t bd0 = b_desc_base + (uint64_t)((st * kT2StageBytes) >> 4);
+                        mbar_wait(bar_full + 8 * st, (it / kT2Stages) & 1);
+                        mbar_wait(my_empty0, (it & 1) ^ 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            tc_mma_f16(d_tmem0, a_desc0, bd0, kT2Idesc, 0);
+                            for (int e = 1; e < k_steps; ++e) tc_mma_f16(d_tmem0, a_desc1, bd0 + (256 >> 4), kT2Idesc, 1);
+                            tc_commit(my_commit + 8 * st);
+                        }
+                        __syncwarp();
+                    }
+                } else
+#endif
+                if (k_steps > 1)
+                    issue_loop(std::true_type{});
+                else
+                    issue_loop(std::false_type{});
+            } else
+#endif
             for (int j = 0; j < sweep; ++j, ++it) {
                 const uint32_t st = it % kT2Stages;
                 const long long q0 = T2_NOW();
@@ -320,16 +350,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 #endif
                 if (elect_one()) {
                     const uint64_t bd0 = b_desc_base + (uint64_t)((st * kT2StageBytes) >> 4);
-                    if (kTS) {
-                        tc_mma_f16_ts(d_tmem, a_tmem, bd0, kT2Idesc, 0);
-                        if (k_steps > 1) tc_mma_f16_ts(d_tmem, a_tmem + 8, bd0 + (256 >> 4), kT2Idesc, 1);
-                    } else {
-                        tc_mma_f16(d_tmem, a_desc0, bd0, kT2Idesc, 0);
-                        if (k_steps > 1) tc_mma_f16(d_tmem, a_desc1, bd0 + (256 >> 4), kT2Idesc, 1);
-                    }
-#ifdef MEPOL_TC2_DBGMODES
-                    for (int e = 2; e < k_steps; ++e) tc_mma_f16(d_tmem, a_desc1, bd0 + (256 >> 4), kT2Idesc, 1);   // timing only
-#endif
+                    tc_mma_f16(d_tmem, a_desc0, bd0, kT2Idesc, 0);
+                    if (k_steps > 1) tc_mma_f16(d_tmem, a_desc1, bd0 + (256 >> 4), kT2Idesc, 1);
                     tc_commit(my_commit + 8 * st);
                 }
                 __syncwarp();
@@ -339,10 +361,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 if (t == 1 && lane == 0) ts_s[8 + (it & 7)] = (uint32_t)T2_NOW();
 #endif
             }
-            if (!kTS) {
-                if (elect_one()) tc_commit(bar_a_empty);   // query tiles reusable once every MMA of the block retired
-                __syncwarp();
-            }
+            if (elect_one()) tc_commit(bar_a_empty);   // query tiles reusable once every MMA of the block retired
+            __syncwarp();
         }
 #ifdef MEPOL_BRINGUP
         if (!kDump && dump && lane == 0) {
@@ -445,26 +465,6 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             const int tiles = unit_of(u, rblk, sp, tile0);
             const int row = rblk * kT2Rows + rloc;
             const bool live = row < n_q;
-            if (kTS) {
-                // This thread's query row -> its TMEM lane (columns 240-255 of the accumulator's half).  Every MMA of
-                // the previous unit has retired: this warp waited for the commit of that unit's last tile.
-                const int r128 = rloc & 127;
-                const uint4 *src = reinterpret_cast<const uint4 *>(qb + ((size_t)rblk * 2 + t) * (kTcTileBytes / 2)) +
-                                   ((r128 >> 3) * 4) * 8 + (r128 & 7);
-                uint32_t a[16];
-#pragma unroll
-                for (int kc = 0; kc < 4; ++kc) {
-                    const uint4 q4 = __ldg(src + kc * 8);
-                    a[4 * kc] = q4.x;
-                    a[4 * kc + 1] = q4.y;
-                    a[4 * kc + 2] = q4.z;
-                    a[4 * kc + 3] = q4.w;
-                }
-                tc_st16(tmem_row + kT2TileRefs, a);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a_full + 8 * t);
-            }
             float tau = live ? INF : -INF;
             // fp16 accumulation: band0 + bandk |t| (c = bound of the accumulator after the first K step)
             // err(s~) = e0 + u_r (c_first + |s~|) + u_i (M1 + M2):  c_first bounds the accumulator after the first
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             uint32_t tau2 = h2_splat_up(tau);
 #pragma unroll
             for (int i = 0; i < (K1 > 0 ? K1 : 1); ++i) topk[i] = INF;
-            const int rot = kDump ? 0 : (rblk * 256 / kT2TileRefs) % tiles;
+            const int rot = kDump ? 0 : (rblk * (256 / NC)) % tiles;
             const int warm = warm_of(tiles), sweep = tiles + warm;
             // Slow path, second half: walk the parked group's mask, append the survivors, keep tau
             // current, compact full buffers.  Called right AFTER the next tile's TMEM load + release,
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 if (kDump) {
                     if (rblk == 0)
 #pragma unroll
-                        for (int r = 0; r < kT2TileRefs / 2; ++r) {
+                        for (int r = 0; r < kRegs; ++r) {
                             const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v[r]));
                             dump[(size_t)rloc * kT2TileRefs + 2 * r] = f.x;
                             dump[(size_t)rloc * kT2TileRefs + 2 * r + 1] = f.y;
@@ -592,12 +592,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     const uint32_t *w = v + 16 * c;
                     const uint32_t m0 = hmin2_3(w[0], w[1], w[2]), m1 = hmin2_3(w[3], w[4], w[5]);
                     const uint32_t m2 = hmin2_3(w[6], w[7], w[8]), m3 = hmin2_3(w[9], w[10], w[11]);
-                    if (kTS && c == kGroups - 1) {      // 16 scores; registers 120-127 are the A operand's columns
-                        gm[c] = hmin2_3(m0, m1, hmin2_2(w[6], w[7]));
-                    } else {
-                        const uint32_t m4 = hmin2_3(w[12], w[13], w[14]);
-                        gm[c] = hmin2_2(hmin2_3(m0, m1, m2), hmin2_3(m3, m4, w[15]));
-                    }
+                    const uint32_t m4 = hmin2_3(w[12], w[13], w[14]);
+                    gm[c] = hmin2_2(hmin2_3(m0, m1, m2), hmin2_3(m3, m4, w[15]));
                     if (c == kGroups / 2 - 1 && !next_ready) {
                         const uint32_t st1 = (it + kFuse) % kT2Stages;
                         next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + kFuse) / kT2Stages) & 1,
@@ -656,10 +652,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj)
                             mask |= (__hlt2_mask(*reinterpret_cast<const __half2 *>(&v[16 * c + jj]), th) & 0x00010001u) << jj;
-                        const int gw = (kTS && c == kGroups - 1) ? 16 : 32;     // scores in this group
-                        if (ref0 + gw > n_ref || gw < 32) {    // padding references / the half group of a 240-wide tile
-                            int nv = n_ref > ref0 ? n_ref - ref0 : 0;
-                            if (nv > gw) nv = gw;
+                        if (ref0 + 32 > n_ref) {               // padding references
+                            const int nv = n_ref > ref0 ? n_ref - ref0 : 0;
                             mask &= ((1u << ((nv + 1) >> 1)) - 1u) | (((1u << (nv >> 1)) - 1u) << 16);
                         }
 #pragma unroll
@@ -739,24 +733,21 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 // a single step and no intermediate rounding)
 static float t2_c_norm_first(int d) { return (d < 16 && d + 3 > 16) ? 1.0f : 0.f; }
 
-int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, bool ts, cudaStream_t st) {
-    auto kern = nc == 256 ? (ts ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 256, 1, true> : knn_prune_tc2_kernel<false, 0, 256, 1, true>)
-                                : (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 256, 1, false> : knn_prune_tc2_kernel<false, 0, 256, 1, false>))
-                : fuse == 2 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 2, false> : knn_prune_tc2_kernel<false, 0, 128, 2, false>)
-                            : (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 1, false> : knn_prune_tc2_kernel<false, 0, 128, 1, false>);
-    const int tile_refs = ts ? kT2TsRefs : nc;
+int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st) {
+    auto kern = nc == 256 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 256, 1> : knn_prune_tc2_kernel<false, 0, 256, 1>)
+                : fuse == 2 ? (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 2> : knn_prune_tc2_kernel<false, 0, 128, 2>)
+                            : (p.k1 == 5 ? knn_prune_tc2_kernel<false, 5, 128, 1> : knn_prune_tc2_kernel<false, 0, 128, 1>);
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemTotal));
     const int n_row_blocks = (int)(p.n_q_pad / kT2Rows);
-    // TS tiles are 240 references wide; n_ref_pad covers the last (partly padded) one (capi.cu)
-    const int n_ref_tiles = ts ? (int)((p.n_ref + tile_refs - 1) / tile_refs) : (int)(p.n_ref_pad / nc);
+    const int n_ref_tiles = (int)(p.n_ref_pad / nc);
     int grid = device_sm_count();
     const int n_full_blocks = p.tc_tail_split > 1 ? (n_row_blocks / grid) * grid : n_row_blocks;
     const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * p.tc_tail_split;
     if (grid > n_units) grid = n_units;
     // Warm-up tiles pay for themselves only on short sweeps (measured, profiles/r02_tc2_notes.md: -5..-8 % at
     // N = 64k-131k, neutral at 512k, +3 % at 1M where the deferred survivor path is cheap enough on its own)
-    int warm_tiles = p.n_ref_pad >= 786432 ? 0 : 256 * 128 / tile_refs;
-    if (const char *wt = getenv("MEPOL_TC_WARM_TILES")) warm_tiles = atoi(wt) * 128 / tile_refs;   // tuning aid; any value >= 0 is exact
+    int warm_tiles = p.n_ref_pad >= 786432 ? 0 : 256 * 128 / nc;
+    if (const char *wt = getenv("MEPOL_TC_WARM_TILES")) warm_tiles = atoi(wt) * 128 / nc;   // tuning aid; any value >= 0 is exact
     if (warm_tiles < 0) warm_tiles = 0;
     float acc_scale = 1.0f;   // experiment knob: scales the fp16-accumulation part of the band (exact only for >= 1)
     if (const char *bs = getenv("MEPOL_TC2_ACC_SCALE")) acc_scale = (float)atof(bs);
@@ -803,7 +794,7 @@ int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, bool ts, cudaStream_t s
 
 // Test hook: raw fp16 accumulator tile (first 256 query rows x first 256 references) as float.
 int launch_tc2_dump(const KnnPlan &p, float *dump, cudaStream_t st) {
-    auto kern = knn_prune_tc2_kernel<true, 0, 256, 1, false>;
+    auto kern = knn_prune_tc2_kernel<true, 0, 256, 1>;
     MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemTotal));
     kern<<<1, kT2Threads, kT2SmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, p.q_ahalf, (int)p.n_q, p.rb, (int)p.n_ref, 1, 1,
                                               p.glob, p.k1, p.cand, p.cand_cnt, p.flag, nullptr, dump, 1, 1, 1, 0,
