@@ -146,7 +146,7 @@ template <int kN> __device__ __forceinline__ void tc_ld_packed_at(uint32_t taddr
 // kFuse = accumulator buffers an epilogue warp unloads per loop iteration (2 only with NC = 128: both
 // 128-column buffers are pulled into 128 registers back to back and filtered as ONE 256-score row, which
 // halves the per-tile fixed costs of the epilogue while the MMAs keep the finer-grained hand-shake)
-template <bool kDump, int K1, int NC, int kFuse>
+template <bool kDump, int K1, int NC, int kFuse, int kDbg = 0>
 __global__ void __launch_bounds__(kT2Threads, 1)
     knn_prune_tc2_kernel(const uint16_t *__restrict__ qb, const float *__restrict__ q_anorm,
                          const float *__restrict__ q_delta, const float *__restrict__ q_ahalf, int n_q,
@@ -155,13 +155,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                          int32_t *__restrict__ cand_cnt, unsigned char *__restrict__ flag,
                          unsigned long long *__restrict__ stats, float *__restrict__ dump, int n_full_blocks,
                          int tail_split, int n_split, int warm_tiles, int k_steps, float c_norm_first, float acc_scale, int dbg_in) {
-#ifdef MEPOL_TC2_DBGMODES
-    // timing experiments of profiles/r02_tc2_notes.md section 7 (results invalid, capi.cu stops after this kernel):
+    // timing experiments of profiles/r02_tc2_notes.md section 7 (results invalid, capi.cu stops after this kernel;
+    // instantiated only with -DMEPOL_TC2_DBGMODES, as a TEMPLATE argument: run-time branches made ptxas spill):
     // 1 = accumulator 1 idle, 2 = no TMEM load, 4 = load + release only, 16 = + min tree, 32 = + vote (no survivor path)
-    const int dbg = dbg_in;
-#else
-    constexpr int dbg = 0;
-#endif
+    constexpr int dbg = kDbg;
+    (void)dbg_in;
     extern __shared__ __align__(1024) unsigned char smem[];
     using Cfg = T2Cfg<NC>;
     constexpr int kT2Stages = Cfg::kStages, kT2StageBytes = Cfg::kStageBytes, kT2TileRefs = NC;
@@ -393,6 +391,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         unsigned long long n_cand = 0;
         bool next_ready = false;
         long long prof[6] = {0, 0, 0, 0, 0, 0};   // bring-up only: cycles in wait / ld / tree / slow, slow entries, tiles
+        long long fast_entries = 0;
+        long long ep[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bring-up only, inside an episode: group vote / mask / park / walk / compaction / tail; groups, drains
         unsigned long long chainE = 0;
 
         float topk[K1 > 0 ? K1 : 1];
@@ -499,10 +499,30 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             unsigned pend_mask = 0;
             int pend_ref0 = 0;
             bool has_pending = false;
+            // kSingle: when no row of the warp has more than one survivor in the group (the rule once tau has
+            // settled: a row's appends are then its final candidates, one at a time), the survivor IS the group's
+            // minimum, which the min tree already holds -- nothing is parked and the walk is one predicated append.
+            constexpr bool kSingle = true;
+            bool pend_single = false;
+            float pend_val = 0.f;
             auto drain = [&]() {
                 const long long pd0 = T2_NOW();
                 unsigned mask = pend_mask;
                 const __half *stg_h = reinterpret_cast<const __half *>(stg + lane * kT2StgStride);
+                ++ep[7];
+                if (kSingle && pend_single) {
+                    if (mask && pend_val < tau) {
+                        const int b = __ffs(mask) - 1;
+                        bufv[my_base + cnt] = pend_val;
+                        bufi[my_base + cnt] = pend_ref0 + 2 * (b & 15) + (b >> 4);
+                        ++cnt;
+                        if (K1 > 0) {
+                            topk_insert(pend_val);
+                            tau = fminf(tau, tau_of(topk[K1 > 0 ? K1 - 1 : 0], band0, bandk));
+                        }
+                    }
+                    mask = 0;
+                }
                 while (mask) {
                     const int b = __ffs(mask) - 1;
                     mask &= mask - 1;
@@ -518,16 +538,22 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                         }
                     }
                 }
+                const long long pd1 = T2_NOW();
                 unsigned full = __ballot_sync(0xffffffffu, cnt > kT2SoftCap);
                 while (full) {
                     const int L = __ffs(full) - 1;
                     full &= full - 1;
                     coop_compact(L, cnt, tau, band0, bandk, ovf);
                 }
+                const long long pd2 = T2_NOW();
                 tau2 = h2_splat_up(tau);
                 __syncwarp();                                  // staging rows are reusable
                 has_pending = false;
-                prof[3] += T2_NOW() - pd0;
+                const long long pd3 = T2_NOW();
+                ep[3] += pd1 - pd0;
+                ep[4] += pd2 - pd1;
+                ep[5] += pd3 - pd2;
+                prof[3] += pd3 - pd0;
             };
             auto tile = [&](auto warm_c, int j) {
                 constexpr bool kWarmTile = decltype(warm_c)::value;
@@ -635,14 +661,60 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     // survivor mask and parks the group in its private staging row (16 packed registers).
                     // The walk, append and compaction are DEFERRED behind the next tile's TMEM load + release,
                     // see drain().
-                    unsigned gbits = 0;
+                    unsigned lg = 0;                 // this row's hit groups
 #pragma unroll
-                    for (int c = 0; c < kGroups; ++c) gbits |= h2_any_lt(gm[c], tau2) ? (1u << c) : 0u;
-                    gbits = __reduce_or_sync(0xffffffffu, gbits);
+                    for (int c = 0; c < kGroups; ++c) lg |= h2_any_lt(gm[c], tau2) ? (1u << c) : 0u;
+                    const unsigned gbits = __reduce_or_sync(0xffffffffu, lg);
+                    ep[0] += T2_NOW() - pt3;
+                    if (kSingle) {
+                        // Common case once tau has settled: every row has at most ONE survivor in the whole tile.  One
+                        // pass over the hit groups builds the masks; a row's survivor is its group minimum (already
+                        // in the min tree), so nothing is parked and the deferred part is one predicated append.
+                        const long long pg0 = T2_NOW();
+                        bool multi = (lg & (lg - 1)) != 0;
+                        unsigned my_mask = 0;
+                        float my_val = 0.f;
+                        int my_ref0 = 0;
+                        const __half2 th = *reinterpret_cast<const __half2 *>(&tau2);
+#pragma unroll
+                        for (int c = 0; c < kGroups; ++c) {
+                            if (!(gbits & (1u << c))) continue;
+                            const int ref0 = jts[c / kSubGroups] * kT2TileRefs + (c % kSubGroups) * 32;
+                            unsigned mask = 0;
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj)
+                                mask |= __hlt2_mask(*reinterpret_cast<const __half2 *>(&v[16 * c + jj]), th) & (0x00010001u << jj);
+                            if (ref0 + 32 > n_ref) {               // padding references
+                                const int nv = n_ref > ref0 ? n_ref - ref0 : 0;
+                                mask &= ((1u << ((nv + 1) >> 1)) - 1u) | (((1u << (nv >> 1)) - 1u) << 16);
+                            }
+                            if (lg & (1u << c)) {
+                                my_mask = mask;
+                                my_val = h2_min_f32(gm[c]);
+                                my_ref0 = ref0;
+                                multi = multi || (mask & (mask - 1)) != 0;
+                            }
+                            ++ep[6];
+                        }
+                        ep[1] += T2_NOW() - pg0;
+                        if (!__any_sync(0xffffffffu, multi)) {
+                            ++fast_entries;
+                            if (has_pending) drain();
+                            pend_single = true;
+                            pend_mask = my_mask;
+                            pend_val = my_val;
+                            pend_ref0 = my_ref0;
+                            has_pending = true;
+                            prof[3] += T2_NOW() - pt3;
+                            return;
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < kGroups; ++c) {
                         if (!(gbits & (1u << c))) continue;
                         if (has_pending) drain();              // a second hit group in one tile (rare)
+                        const long long pg0 = T2_NOW();
+                        ++ep[6];
                         const int ref0 = jts[c / kSubGroups] * kT2TileRefs + (c % kSubGroups) * 32;
                         // bit j = score 2j, bit 16+j = score 2j+1.  tau2 is tau rounded UP to fp16, so the
                         // mask is a superset of the survivors; the walk compares exactly.  (Building the mask
@@ -650,17 +722,26 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                         unsigned mask = 0;
                         const __half2 th = *reinterpret_cast<const __half2 *>(&tau2);
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj)
-                            mask |= (__hlt2_mask(*reinterpret_cast<const __half2 *>(&v[16 * c + jj]), th) & 0x00010001u) << jj;
+                        for (int jj = 0; jj < 16; ++jj) {
+                            // __hlt2_mask gives 0xffff / 0 per half: one AND with the pair's two bit positions
+                            if (kSingle)
+                                mask |= __hlt2_mask(*reinterpret_cast<const __half2 *>(&v[16 * c + jj]), th) & (0x00010001u << jj);
+                            else
+                                mask |= (__hlt2_mask(*reinterpret_cast<const __half2 *>(&v[16 * c + jj]), th) & 0x00010001u) << jj;
+                        }
                         if (ref0 + 32 > n_ref) {               // padding references
                             const int nv = n_ref > ref0 ? n_ref - ref0 : 0;
                             mask &= ((1u << ((nv + 1) >> 1)) - 1u) | (((1u << (nv >> 1)) - 1u) << 16);
                         }
+                        const long long pg1 = T2_NOW();
+                        ep[1] += pg1 - pg0;
+                        pend_single = false;
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) stg[lane * kT2StgStride + jj] = v[16 * c + jj];
                         pend_mask = mask;
                         pend_ref0 = ref0;
                         has_pending = true;
+                        ep[2] += T2_NOW() - pg1;
                     }
                     prof[3] += T2_NOW() - pt3;
                 }
@@ -704,6 +785,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 #ifdef MEPOL_BRINGUP
         if (!kDump && dump && lane == 0)
             for (int i = 0; i < 6; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + i, (unsigned long long)prof[i]);
+        if (!kDump && dump && lane == 0)
+        {
+            for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 16 + i, (unsigned long long)ep[i]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 24, (unsigned long long)fast_entries);
+        }
         if (!kDump && dump && warp == 7 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(dump) + 13, chainE);
 #endif
         if (!kDump && stats) {
@@ -744,9 +830,10 @@ int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st) {
     const int n_full_blocks = p.tc_tail_split > 1 ? (n_row_blocks / grid) * grid : n_row_blocks;
     const int n_units = n_full_blocks + (n_row_blocks - n_full_blocks) * p.tc_tail_split;
     if (grid > n_units) grid = n_units;
-    // Warm-up tiles pay for themselves only on short sweeps (measured, profiles/r02_tc2_notes.md: -5..-8 % at
-    // N = 64k-131k, neutral at 512k, +3 % at 1M where the deferred survivor path is cheap enough on its own)
-    int warm_tiles = p.n_ref_pad >= 786432 ? 0 : 256 * 128 / nc;
+    // Warm-up tiles (32,768 references) shorten the expensive part of a sweep, the ramp in which every score is a
+    // survivor: -20 % at N = 64k-131k, -10 % at 262k, -6 % at 512k, -1.2 % at 1M (profiles/r02_tc2_notes.md section 8;
+    // 128 or 384-512 x 128 references measured worse at every size)
+    int warm_tiles = 256 * 128 / nc;
     if (const char *wt = getenv("MEPOL_TC_WARM_TILES")) warm_tiles = atoi(wt) * 128 / nc;   // tuning aid; any value >= 0 is exact
     if (warm_tiles < 0) warm_tiles = 0;
     float acc_scale = 1.0f;   // experiment knob: scales the fp16-accumulation part of the band (exact only for >= 1)
@@ -762,9 +849,24 @@ int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st) {
 #ifdef MEPOL_BRINGUP
     static unsigned long long *prof_buf = nullptr;
     if (getenv("MEPOL_TC_PROF")) {
-        if (!prof_buf) cudaMalloc(&prof_buf, 128);
-        cudaMemsetAsync(prof_buf, 0, 128, st);
+        if (!prof_buf) cudaMalloc(&prof_buf, 256);
+        cudaMemsetAsync(prof_buf, 0, 256, st);
         prof_dev = reinterpret_cast<float *>(prof_buf);
+    }
+#endif
+#ifdef MEPOL_TC2_DBGMODES
+    if (nc == 256 && p.k1 == 5) {
+        switch (dbg) {
+            case 1: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 1>; break;
+            case 2: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 2>; break;
+            case 4: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 4>; break;
+            case 5: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 5>; break;
+            case 16: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 16>; break;
+            case 32: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 32>; break;
+            case 33: kern = knn_prune_tc2_kernel<false, 5, 256, 1, 33>; break;
+            default: break;
+        }
+        if (dbg) MEPOL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kT2SmemTotal));
     }
 #endif
     kern<<<grid, kT2Threads, kT2SmemTotal, st>>>(p.qb, p.q_anorm, p.q_delta, p.q_ahalf, (int)p.n_q, p.rb, (int)p.n_ref,
@@ -774,12 +876,17 @@ int launch_prune_tc2(const KnnPlan &p, int nc, int fuse, cudaStream_t st) {
     MEPOL_CUDA_CHECK(cudaGetLastError());
 #ifdef MEPOL_BRINGUP
     if (prof_dev) {
-        unsigned long long h[16];
+        unsigned long long h[32];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost);
         const double w = (double)grid * kT2EpiWarps, tl = (double)h[5] / w;
         fprintf(stderr, "[tc2 prof] per epilogue warp: tiles %.0f  cycles/tile: wait %.1f ld+release %.1f tree %.1f slow %.1f  slow entries/tile %.4f  cycles/entry %.0f\n",
                 tl, h[0] / w / tl, h[1] / w / tl, h[2] / w / tl, h[3] / w / tl, (double)h[4] / h[5], h[4] ? (double)h[3] / h[4] : 0.0);
+        if (h[4]) fprintf(stderr, "[tc2 episode] %.1f %% of the slow entries took the single-survivor path\n", 100.0 * h[24] / h[4]);
+        if (h[4])
+            fprintf(stderr, "[tc2 episode] cycles per slow entry: group vote %.0f; per hit group (%.2f per entry): mask %.0f park %.0f; per drain (%.2f per entry): walk %.0f compaction %.0f tail %.0f\n",
+                    (double)h[16] / h[4], (double)h[22] / h[4], h[22] ? (double)h[17] / h[22] : 0.0, h[22] ? (double)h[18] / h[22] : 0.0,
+                    (double)h[23] / h[4], h[23] ? (double)h[19] / h[23] : 0.0, h[23] ? (double)h[20] / h[23] : 0.0, h[23] ? (double)h[21] / h[23] : 0.0);
         for (int t = 0; t < 2; ++t)
             if (h[8 + 3 * t])
                 fprintf(stderr, "[tc2 prof] issuer %d: cycles/tile: wait (stage + accumulator) %.1f  fence+issue %.1f\n", t,
