@@ -284,8 +284,8 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
                                              cudaMemcpyDeviceToDevice, st));
         return MEPOL_OK;
     }
-    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
-    if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, false, st)) != MEPOL_OK) return rc;
+    if ((p.algo == MEPOL_KNN_TC || !p.q_is_ref) && (rc = launch_pack(q, n_q, d, p, false, false, st)) != MEPOL_OK) return rc;
     prof_record(0, st);
     if (p.algo == MEPOL_KNN_TC)
         {
@@ -297,8 +297,13 @@ extern "C" int mepol_knn_search_f32(const float *ref, int64_t n_ref, const float
         rc = launch_prune_simt(p, st);
     prof_record(1, st);
     if (rc != MEPOL_OK) return rc;
-    // rows whose fp16 band overflowed are re-pruned with the fp32 band before the exact fallback
-    if (p.algo == MEPOL_KNN_TC && (rc = launch_rescue_simt(p, st)) != MEPOL_OK) return rc;
+    // rows whose fp16 band overflowed are re-pruned with the fp32 band before the exact fallback (the fp32 operands
+    // of that pass are only produced when it is going to run: both launches exit at once otherwise)
+    if (p.algo == MEPOL_KNN_TC) {
+        if ((rc = launch_pack(ref, n_ref, d, p, true, true, st)) != MEPOL_OK) return rc;
+        if (!p.q_is_ref && (rc = launch_pack(q, n_q, d, p, false, true, st)) != MEPOL_OK) return rc;
+        if ((rc = launch_rescue_simt(p, st)) != MEPOL_OK) return rc;
+    }
 #ifdef MEPOL_TC2_DBGMODES
     if (getenv("MEPOL_TC2_DBG") || getenv("MEPOL_TC2_KSTEPS")) return MEPOL_OK;   // timing experiments: scores are invalid, stop here
 #endif
@@ -328,8 +333,8 @@ extern "C" int mepol_debug_tc_scores(const float *ref, int64_t n_ref, const floa
                   workspace_bytes, p.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
-    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
-    if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, false, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(q, n_q, d, p, false, false, st)) != MEPOL_OK) return rc;
     return launch_tc_dump(p, out, st);
 }
 
@@ -345,8 +350,8 @@ extern "C" int mepol_debug_tc2_scores(const float *ref, int64_t n_ref, const flo
                   workspace_bytes, p.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = launch_col_mean(ref, n_ref, d, p, st)) != MEPOL_OK) return rc;
-    if ((rc = launch_pack(ref, n_ref, d, p, true, st)) != MEPOL_OK) return rc;
-    if ((rc = launch_pack(q, n_q, d, p, false, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(ref, n_ref, d, p, true, false, st)) != MEPOL_OK) return rc;
+    if ((rc = launch_pack(q, n_q, d, p, false, false, st)) != MEPOL_OK) return rc;
     return launch_tc2_dump(p, out, st);
 }
 

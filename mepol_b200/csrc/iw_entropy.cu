@@ -109,6 +109,67 @@ __device__ __forceinline__ double block_reduce_max(double v, double *s_warp) {
     return t;
 }
 
+
+// exp / log at the STORAGE precision of the log-probs (fp32 kernels: MUFU-based expf / logf; sums stay in float64)
+template <typename T>
+struct RowMath;
+template <>
+struct RowMath<float> {
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+};
+template <>
+struct RowMath<double> {
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+};
+
+// Last-block fold of the per-trajectory (max, sum exp(c - max)) pairs into scal[3] (M), scal[4] (S), scal[6],
+// in a fixed order (deterministic).  L2 loads (ld.global.cg: the pairs were written by other CTAs), unrolled so
+// that a thread's loads are in flight together -- the volatile loops of the first version were chains of
+// ~700-cycle round trips (9 + 18 of them for 2098 trajectories): microseconds of single-CTA tail.
+__device__ __forceinline__ void fold_traj_pairs(const double *__restrict__ traj_max, const double *__restrict__ traj_sum,
+                                                int n_traj, double *s_warp, double *s_bcast, double *__restrict__ scal) {
+    const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
+    constexpr int kU = 8;
+    const int nthr = blockDim.x;
+    double gm = NEG_INF;
+    for (int i0 = threadIdx.x; i0 < n_traj; i0 += kU * nthr) {
+        double tm[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tm[u] = (i0 + u * nthr < n_traj) ? __ldcg(traj_max + i0 + u * nthr) : NEG_INF;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) gm = fmax(gm, tm[u]);
+    }
+    gm = block_reduce_max(gm, s_warp);
+    if (threadIdx.x == 0) *s_bcast = gm;
+    __syncthreads();
+    gm = *s_bcast;
+    double gs = 0.0;
+    for (int i0 = threadIdx.x; i0 < n_traj; i0 += kU * nthr) {
+        double tm[kU], ts[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const bool ok = i0 + u * nthr < n_traj;
+            tm[u] = ok ? __ldcg(traj_max + i0 + u * nthr) : NEG_INF;
+            ts[u] = ok ? __ldcg(traj_sum + i0 + u * nthr) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (ts[u] != 0.0) gs += ts[u] * exp(tm[u] - gm);   // empty trajectories contribute 0 (NaN != 0 propagates)
+    }
+    gs = block_reduce_sum(gs, s_warp);
+    if (threadIdx.x == 0) {
+        scal[3] = gm;
+        scal[4] = gs;
+        // The reference forms exp(cumsum) directly in float64 (mepol.py:130): it overflows to inf
+        // (-> inf/inf = nan weights) above log(DBL_MAX) and the whole batch underflows to 0/0 below
+        // log(min subnormal).  The stabilised form here would silently survive; keep the reference's
+        // numeric-error behaviour by flagging those regimes.
+        scal[6] = (gm > 709.782712893384 || gm < -745.1332191019412) ? 1.0 : 0.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------ K2a scan
 template <typename T>
 __global__ void __launch_bounds__(kScanThreads)
@@ -154,48 +215,14 @@ __global__ void __launch_bounds__(kScanThreads)
     if (s_ticket != (unsigned)(n_traj - 1)) return;
     // last CTA: fold per-trajectory (max, sum) pairs in fixed order
     __threadfence();
-    double gm = NEG_INF;
-    for (int i = threadIdx.x; i < n_traj; i += kScanThreads) {
-        const double tm = ((volatile double *)traj_max)[i];
-        gm = fmax(gm, tm);
-    }
-    gm = block_reduce_max(gm, s_warp);
-    if (threadIdx.x == 0) s_bcast = gm;
-    __syncthreads();
-    gm = s_bcast;
-    double gs = 0.0;
-    for (int i = threadIdx.x; i < n_traj; i += kScanThreads) {
-        const double tm = ((volatile double *)traj_max)[i];
-        const double ts = ((volatile double *)traj_sum)[i];
-        if (ts != 0.0) gs += ts * exp(tm - gm);   // empty trajectories contribute 0 (NaN != 0 propagates)
-    }
-    gs = block_reduce_sum(gs, s_warp);
-    if (threadIdx.x == 0) {
-        scal[3] = gm;
-        scal[4] = gs;
-        // The reference forms exp(cumsum) directly in float64 (mepol.py:130): it overflows to inf
-        // (-> inf/inf = nan weights) above log(DBL_MAX) and the whole batch underflows to 0/0 below
-        // log(min subnormal).  The stabilised form here would silently survive; keep the reference's
-        // numeric-error behaviour by flagging those regimes.
-        scal[6] = (gm > 709.782712893384 || gm < -745.1332191019412) ? 1.0 : 0.0;
-    }
+    fold_traj_pairs(traj_max, traj_sum, n_traj, s_warp, &s_bcast, scal);
 }
 
 // ---------------------------------------------------------------------------------- K2b gather
-template <typename T>
-struct RowMath;
-template <>
-struct RowMath<float> {
-    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
-    static __device__ __forceinline__ float log_(float x) { return logf(x); }
-};
-template <>
-struct RowMath<double> {
-    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
-    static __device__ __forceinline__ double log_(double x) { return log(x); }
-};
-
-template <typename T>
+// KT = k when it is known at compile time (4: every shipped configuration but GridWorld), 0 = run-time loop.  With a
+// run-time trip count the index and weight loads of a row form a chain; unrolled, a thread has kGatherRows * k
+// index loads and then as many gathers in flight.
+template <typename T, int KT>
 __global__ void __launch_bounds__(kGatherThreads)
     iw_gather_kernel(const T *__restrict__ c, const int32_t *__restrict__ idx, int k1, int n,
                      const T *__restrict__ rk, int ns, double log_G, double B, double eps,
@@ -220,7 +247,18 @@ __global__ void __launch_bounds__(kGatherThreads)
         if (i < n) {
             const int32_t *ir = idx + (size_t)i * k1;
             double W = 0.0;
-            for (int m = 0; m < k; ++m) W += (double)RowMath<T>::exp_(c[ir[m]] - Mt);   // storage-precision exp, fp64 sum
+            if (KT > 0) {
+                int nb[KT > 0 ? KT : 1];
+                T cv[KT > 0 ? KT : 1];
+#pragma unroll
+                for (int m = 0; m < KT; ++m) nb[m] = ir[m];
+#pragma unroll
+                for (int m = 0; m < KT; ++m) cv[m] = c[nb[m]];
+#pragma unroll
+                for (int m = 0; m < KT; ++m) W += (double)RowMath<T>::exp_(cv[m] - Mt);   // storage-precision exp, fp64 sum
+            } else {
+                for (int m = 0; m < k; ++m) W += (double)RowMath<T>::exp_(c[ir[m]] - Mt);
+            }
             Wr[r] = W * inv_S;
         }
     }
@@ -270,12 +308,25 @@ __global__ void __launch_bounds__(kGatherThreads)
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += kGatherThreads) {
-        const volatile double *pp = blk_part + (size_t)b * 4;
-        a0 += pp[0];
-        a1 += pp[1];
-        a2 += pp[2];
-        a3 += pp[3];
+    {   // L2 loads, four blocks' partials in flight per thread (see fold_traj_pairs)
+        constexpr int kU = 4;
+        for (unsigned b0 = threadIdx.x; b0 < gridDim.x; b0 += kU * kGatherThreads) {
+            double2 lo2[kU], hi2[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const unsigned b = b0 + u * kGatherThreads;
+                const double2 *pp = reinterpret_cast<const double2 *>(blk_part + (size_t)b * 4);
+                lo2[u] = b < gridDim.x ? __ldcg(pp) : make_double2(0.0, 0.0);
+                hi2[u] = b < gridDim.x ? __ldcg(pp + 1) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                a0 += lo2[u].x;
+                a1 += lo2[u].y;
+                a2 += hi2[u].x;
+                a3 += hi2[u].y;
+            }
+        }
     }
     a0 = block_reduce_sum(a0, s_warp);
     a1 = block_reduce_sum(a1, s_warp);
@@ -326,10 +377,14 @@ __global__ void __launch_bounds__(kScanThreads)
 
 // ---------------------------------------------------------------- warp-per-trajectory variants
 // With thousands of short trajectories (the N=1M benchmark has 2098 of length 500) a CTA per
-// trajectory spends its time in __syncthreads; here one warp scans one trajectory in 32-element
-// chunks with shuffles only, four chunks of loads in flight, and keeps a running (max, sum exp)
-// pair per lane so the trajectory is read exactly once.
+// trajectory spends its time in __syncthreads; here one warp scans one trajectory with shuffles only.
+// Each lane owns kLaneChunk CONSECUTIVE steps (16-byte vector loads / stores): the prefix inside a
+// chunk is a register-local chain, ONE warp scan of the 32 chunk totals per 512 steps links them
+// (the first version ran a 5-stage shuffle scan per 32 steps: sixteen dependent scans per trajectory
+// with 14 warps per SM to hide them, 22 us for 8 MB), and the chunk's (max, sum exp) is formed from
+// registers with independent exps.  The trajectory is read exactly once.
 constexpr int kWarpScanWarps = 8;
+constexpr int kLaneChunk = 16;
 
 __device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
 #pragma unroll
@@ -338,6 +393,46 @@ __device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
         if (lane >= o) v += t;
     }
     return v;
+}
+
+// out[u] = p[j0 + u] for j0 + u in [lo_valid, hi_valid), 0 elsewhere; 16-byte vectors when the whole chunk is
+// inside the range and aligned (trajectory offsets are multiples of 4 in every shipped configuration)
+template <typename T>
+__device__ __forceinline__ void load_chunk(const T *__restrict__ p, int j0, int lo_valid, int hi_valid, T (&out)[kLaneChunk]) {
+    constexpr int V = 16 / (int)sizeof(T);
+    if (j0 >= lo_valid && j0 + kLaneChunk <= hi_valid && (reinterpret_cast<uintptr_t>(p + j0) & 15) == 0) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p + j0);
+#pragma unroll
+        for (int v = 0; v < kLaneChunk / V; ++v) {
+            const uint4 r = q[v];
+            memcpy(&out[v * V], &r, 16);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kLaneChunk; ++u) {
+            const int jj = j0 + u;
+            out[u] = (jj >= lo_valid && jj < hi_valid) ? p[jj] : (T)0;
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_chunk(T *__restrict__ p, int j0, int lo_valid, int hi_valid, const T (&in)[kLaneChunk]) {
+    constexpr int V = 16 / (int)sizeof(T);
+    if (j0 >= lo_valid && j0 + kLaneChunk <= hi_valid && (reinterpret_cast<uintptr_t>(p + j0) & 15) == 0) {
+        uint4 *q = reinterpret_cast<uint4 *>(p + j0);
+#pragma unroll
+        for (int v = 0; v < kLaneChunk / V; ++v) {
+            uint4 r;
+            memcpy(&r, &in[v * V], 16);
+            q[v] = r;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kLaneChunk; ++u) {
+            const int jj = j0 + u;
+            if (jj >= lo_valid && jj < hi_valid) p[jj] = in[u];
+        }
+    }
 }
 
 template <typename T>
@@ -354,34 +449,40 @@ __global__ void __launch_bounds__(kWarpScanWarps * 32)
     if (t < n_traj) {
         const int lo = traj_off[t], hi = traj_off[t + 1];
         double carry = 0.0, m = NEG_INF, ssum = 0.0;
-        for (int base = lo; base < hi; base += 128) {
-            double dv[4];
+        for (int base = lo; base < hi; base += 32 * kLaneChunk) {
+            const int j0 = base + lane * kLaneChunk;
+            T a[kLaneChunk], b[kLaneChunk];
+            load_chunk(lt, j0, lo, hi, a);
+            load_chunk(lb, j0, lo, hi, b);
+            double pre[kLaneChunk];
+            pre[0] = (double)a[0] - (double)b[0];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = base + 32 * u + lane;
-                dv[u] = j < hi ? (double)lt[j] - (double)lb[j] : 0.0;
-            }
+            for (int u = 1; u < kLaneChunk; ++u) pre[u] = pre[u - 1] + ((double)a[u] - (double)b[u]);
+            const double incl = warp_inclusive_scan(pre[kLaneChunk - 1], lane);
+            const double off = incl - pre[kLaneChunk - 1] + carry;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            T stored[kLaneChunk];
+            double lm = NEG_INF;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = base + 32 * u + lane;
-                const double incl = warp_inclusive_scan(dv[u], lane) + carry;
-                carry = __shfl_sync(0xffffffffu, incl, 31);
-                if (j < hi) {
-                    const T stored = (T)incl;
-                    c_out[j] = stored;
-                    const double cv = (double)stored;
-                    if (cv > m) {           // online (max, sum exp(c - max)); NaN falls through to the sum
-                        ssum = ssum * exp(m - cv) + 1.0;
-                        m = cv;
-                    } else {
-                        ssum += exp(cv - m);
-                    }
-                }
+            for (int u = 0; u < kLaneChunk; ++u) {
+                stored[u] = (T)(pre[u] + off);
+                if (j0 + u < hi) lm = fmax(lm, (double)stored[u]);    // NaN is ignored here and poisons the sum below
             }
+            store_chunk(c_out, j0, lo, hi, stored);
+            if (lm > m) {               // rescale the running (max, sum exp(c - max)) pair
+                ssum *= exp(m - lm);
+                m = lm;
+            }
+            // storage-precision exp like the gather kernel's weights (a float64 exp per step was half of this kernel in
+            // the fp32 build: 13.4 -> see profiles/); the difference c - max is formed in float64 first
+#pragma unroll
+            for (int u = 0; u < kLaneChunk; ++u)
+                if (j0 + u < hi) ssum += (double)RowMath<T>::exp_((T)((double)stored[u] - m));
         }
         // fold the 32 (max, sum) pairs
         const double wm = warp_max(m);
-        const double part = warp_sum(m == NEG_INF ? 0.0 : ssum * exp(m - wm));
+        // a lane without steps contributes 0; a lane that only saw NaN (m still -inf, sum NaN) keeps its NaN
+        const double part = warp_sum(m == NEG_INF ? (ssum != ssum ? ssum : 0.0) : ssum * exp(m - wm));
         if (lane == 0) {
             traj_max[t] = wm;
             traj_sum[t] = (hi > lo) ? part : 0.0;
@@ -396,24 +497,7 @@ __global__ void __launch_bounds__(kWarpScanWarps * 32)
     if (s_ticket != gridDim.x - 1) return;
     // last CTA: fold per-trajectory (max, sum) pairs in fixed order
     __threadfence();
-    double gm = NEG_INF;
-    for (int i = threadIdx.x; i < n_traj; i += blockDim.x) gm = fmax(gm, ((volatile double *)traj_max)[i]);
-    gm = block_reduce_max(gm, s_warp);
-    if (threadIdx.x == 0) s_bcast = gm;
-    __syncthreads();
-    gm = s_bcast;
-    double gs = 0.0;
-    for (int i = threadIdx.x; i < n_traj; i += blockDim.x) {
-        const double tm = ((volatile double *)traj_max)[i];
-        const double ts = ((volatile double *)traj_sum)[i];
-        if (ts != 0.0) gs += ts * exp(tm - gm);
-    }
-    gs = block_reduce_sum(gs, s_warp);
-    if (threadIdx.x == 0) {
-        scal[3] = gm;
-        scal[4] = gs;
-        scal[6] = (gm > 709.782712893384 || gm < -745.1332191019412) ? 1.0 : 0.0;   // see iw_scan_kernel
-    }
+    fold_traj_pairs(traj_max, traj_sum, n_traj, s_warp, &s_bcast, scal);
 }
 
 // Backward in the many-trajectories regime, two launches:
@@ -424,6 +508,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     iw_bwd_elem_kernel(const T *__restrict__ c, const T *__restrict__ gW, const double *__restrict__ scal, int n,
                        const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, T *__restrict__ gc_out) {
+    // (Two particles per thread with the rowptr / col / gW loads of a level issued together measured SLOWER, 20.1 vs
+    // 18.6 us at N = 1M: the kernel is paced by the 4 M random 4-byte gathers, a 32-byte L2 sector each, not by the
+    // dependent round trips.)
     const int j = blockIdx.x * 256 + threadIdx.x;
     if (j >= n) return;
     const double M = scal[3], S = scal[4], s = scal[2];
@@ -444,21 +531,21 @@ __global__ void __launch_bounds__(kWarpScanWarps * 32)
     const int lo = traj_off[t], hi = traj_off[t + 1];
     const double gH = grad_H[0];
     double carry = 0.0;
-    // walk backwards: position p = 0 is the LAST step of the trajectory
-    for (int base = 0; base < hi - lo; base += 128) {
-        double gc[4];
+    // walk backwards in blocks of 512 steps; lane 0 owns the LAST kLaneChunk steps of a block
+    for (int top = hi; top > lo; top -= 32 * kLaneChunk) {
+        const int j0 = top - (lane + 1) * kLaneChunk;       // the lane's chunk is [j0, j0 + kLaneChunk), clipped at lo
+        T v[kLaneChunk];
+        load_chunk(g, j0, lo, hi, v);
+        double suf[kLaneChunk];                              // suffix sums inside the chunk
+        suf[kLaneChunk - 1] = (double)v[kLaneChunk - 1];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = hi - 1 - (base + 32 * u + lane);
-            gc[u] = j >= lo ? (double)g[j] : 0.0;
-        }
+        for (int u = kLaneChunk - 2; u >= 0; --u) suf[u] = suf[u + 1] + (double)v[u];
+        const double incl = warp_inclusive_scan(suf[0], lane);   // lanes in walking order: lane 0 first
+        const double off = incl - suf[0] + carry;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = hi - 1 - (base + 32 * u + lane);
-            const double incl = warp_inclusive_scan(gc[u], lane) + carry;
-            carry = __shfl_sync(0xffffffffu, incl, 31);
-            if (j >= lo) g[j] = (T)(gH * incl);
-        }
+        for (int u = 0; u < kLaneChunk; ++u) v[u] = (T)(gH * (suf[u] + off));
+        store_chunk(g, j0, lo, hi, v);
     }
 }
 
@@ -718,7 +805,8 @@ static int iw_fwd_impl(const T *lt, const T *lb, const int32_t *traj_off, int64_
     else
         iw_scan_kernel<T><<<(int)n_traj, kScanThreads, 0, st>>>(lt, lb, traj_off, (int)n_traj, c, w.traj_max,
                                                                 w.traj_sum, w.counters, scal);
-    iw_gather_kernel<T><<<gather_blocks_for(n), kGatherThreads, 0, st>>>(
+    auto gather = k1 == 5 ? iw_gather_kernel<T, 4> : iw_gather_kernel<T, 0>;
+    gather<<<gather_blocks_for(n), kGatherThreads, 0, st>>>(
         c, idx, k1, (int)n, rk, ns, log_G, B, eps, gW, w.blk_part, w.counters, scal,
         log((double)(k1 - 1)) - log((double)n), 0.5 * (double)ns * kLogPi - log_G);
     MEPOL_CUDA_CHECK(cudaGetLastError());

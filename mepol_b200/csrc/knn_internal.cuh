@@ -64,7 +64,17 @@ int knn_make_plan(KnnPlan &p, const float *ref, int64_t n_ref, const float *q, i
 
 // knn_prep.cu
 int launch_col_mean(const float *ref, int64_t n_ref, int d, const KnnPlan &p, cudaStream_t st);
-int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, cudaStream_t st);
+int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, bool lazy, cudaStream_t st);
+// Rescue or fallback?  The chunk-parallel exact fallback streams every reference k1 times per flagged
+// row (~F * k1 * n_ref * d); one rescue sweep costs about a SIMT pass over the row blocks that hold a
+// flagged row (<= n_q * n_ref * d).  The sweep wins once F * k1 exceeds ~n_q / 8; below that, and always
+// within what the fallback's scratch holds, the flagged rows stay with the fallback.
+inline unsigned long long rescue_min_rows(const KnnPlan &p) {
+    long long thr = p.n_q / (8LL * p.k1);
+    if (thr < 64) thr = 64;
+    if (thr > p.fb_max_rows) thr = p.fb_max_rows;
+    return (unsigned long long)thr;
+}
 // knn_simt.cu
 int launch_prune_simt(const KnnPlan &p, cudaStream_t st);
 int launch_rescue_simt(const KnnPlan &p, cudaStream_t st);

@@ -140,7 +140,11 @@ __global__ void __launch_bounds__(kPackRows)
     pack_rows_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int d, int dpad,
                      const double *__restrict__ mean, float *__restrict__ xs, float *__restrict__ nrm,
                      float *__restrict__ anorm, uint16_t *__restrict__ xb, float *__restrict__ delta,
-                     float *__restrict__ ahalf, float *__restrict__ glob, int is_ref) {
+                     float *__restrict__ ahalf, float *__restrict__ glob, int is_ref,
+                     const unsigned long long *__restrict__ gate, unsigned long long gate_min) {
+    // lazy launch (fp32 operands of the rescue pass behind the tensor-core pruner): nothing to do unless the pruner
+    // flagged more rows than the exact fallback takes (the same test knn_prune_simt_kernel makes in rescue mode)
+    if (gate && *gate <= gate_min) return;
     extern __shared__ __align__(16) unsigned char pack_smem[];
     __shared__ double smean[MEPOL_MAX_DIM];
     float *s_in = reinterpret_cast<float *>(pack_smem);                         // [128][d]
@@ -252,8 +256,12 @@ __global__ void __launch_bounds__(kPackRows)
     }
 }
 
-int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, cudaStream_t st) {
-    const bool tc = (p.algo == MEPOL_KNN_TC);
+// lazy = false: the operands of the search itself (SIMT: fp32 rows + norms; tensor-core: fp16 operand tiles + norms).
+// lazy = true (tensor-core searches only): the fp32 rows + norms the RESCUE pass reads, produced behind the pruning
+//   kernel and only when it flagged enough rows (device-side gate) -- on the usual search that is 128 B per row of
+//   writes that nobody reads (134 MB at N = 1M, on every rank of a sharded search).
+int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref, bool lazy, cudaStream_t st) {
+    const bool tc = (p.algo == MEPOL_KNN_TC) && !lazy;
     int64_t n_pad = is_ref ? p.n_ref_pad : p.n_q_pad;
     if (!tc) n_pad = n;
     const int64_t rows = n_pad > n ? n_pad : n;
@@ -264,11 +272,13 @@ int launch_pack(const float *x, int64_t n, int d, const KnnPlan &p, bool is_ref,
     // fp32 operands are produced in both modes (SIMT search / rescue pass); query rows that alias
     // the fitted matrix reuse the reference rows
     float *xs = is_ref ? p.rs : (p.q_is_ref ? nullptr : p.qs);
+    float *nrm = is_ref ? p.r_nrm : nullptr;
+    if (tc) xs = nrm = nullptr;      // produced lazily, see above
     pack_rows_kernel<<<blocks, kPackRows, smem, st>>>(
-        x, n, n_pad, d, p.dpad, p.mean, xs, is_ref ? p.r_nrm : nullptr,
+        x, n, n_pad, d, p.dpad, p.mean, xs, nrm,
         is_ref ? p.r_anorm : p.q_anorm, tc ? (is_ref ? p.rb : p.qb) : nullptr,
         tc ? (is_ref ? nullptr : p.q_delta) : nullptr, tc ? (is_ref ? nullptr : p.q_ahalf) : nullptr, p.glob,
-        is_ref ? 1 : 0);
+        is_ref ? 1 : 0, lazy ? p.stats + 3 : nullptr, lazy ? rescue_min_rows(p) : 0ULL);
     MEPOL_CUDA_CHECK(cudaGetLastError());
     return MEPOL_OK;
 }

@@ -277,17 +277,6 @@ __global__ void __launch_bounds__(kSimtThreads)
     }
 }
 
-// Rescue or fallback?  The chunk-parallel exact fallback streams every reference k1 times per flagged
-// row (~F * k1 * n_ref * d); one rescue sweep costs about a SIMT pass over the row blocks that hold a
-// flagged row (<= n_q * n_ref * d).  The sweep wins once F * k1 exceeds ~n_q / 8; below that, and always
-// within what the fallback's scratch holds, the flagged rows stay with the fallback.
-static unsigned long long rescue_min_rows(const KnnPlan &p) {
-    long long thr = p.n_q / (8LL * p.k1);
-    if (thr < 64) thr = 64;
-    if (thr > p.fb_max_rows) thr = p.fb_max_rows;
-    return (unsigned long long)thr;
-}
-
 template <int DPAD, int ROWS>
 static int launch_simt_inst(const KnnPlan &p, int n_split, int cap, int rescue, cudaStream_t st) {
     const int R = kSimtThreads * ROWS;

@@ -28,3 +28,15 @@ for _ in range(3):
                                             gr.data_ptr(), sp), "bwd")
 torch.cuda.synchronize()
 print("H", sc[0].item(), "KL", sc[1].item())
+if "--prof" in sys.argv:      # per-kernel device times (CUPTI), 20 forward + backward pairs
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(20):
+            _lib.check(lib.mepol_iw_entropy_fwd_f32(lt.data_ptr(), lb.data_ptr(), off.data_ptr(), nt, n, idx.data_ptr(), k + 1, rk32.data_ptr(), d, G, 0.1, 0.0,
+                                                    c.data_ptr(), gw.data_ptr(), sc.data_ptr(), ws.data_ptr(), ws.numel(), sp), "fwd")
+            _lib.check(lib.mepol_iw_entropy_bwd_f32(c.data_ptr(), gw.data_ptr(), sc.data_ptr(), off.data_ptr(), nt, n, rowptr.data_ptr(), col.data_ptr(), one.data_ptr(),
+                                                    gr.data_ptr(), sp), "bwd")
+        torch.cuda.synchronize()
+    for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
+        if e.device_time_total > 0:
+            print(f"{e.key[:70]:70s} n={e.count:3d} mean_us={e.device_time_total / e.count:8.2f}")
