@@ -577,6 +577,23 @@ def run_ours(args):
             lt_dev.grad = None
             H.backward()
         comp["iw_fwd_bwd_ms"] = t_of(fb, 10)
+        # the same forward + backward replayed as ONE CUDA graph -- what entropy.policy_update does in production (the
+        # eager autograd call is host-bound: ~0.2-0.35 ms of Python per evaluation around 0.06 ms of kernels)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fb()
+                fb()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fb()
+            graph.replay()
+            comp["iw_fwd_bwd_graph_ms"] = t_of(graph.replay, 20)
+        except Exception as e:      # explanatory number only
+            comp["iw_fwd_bwd_graph_ms"] = None
+            comp["iw_fwd_bwd_graph_error"] = repr(e)[:200]
         # the kernels alone, straight through the C ABI with pre-allocated buffers (no autograd / allocator)
         lib = _lib.load()
         c_b = torch.empty(n, dtype=torch.float32, device=dev)
@@ -619,6 +636,8 @@ def run_ours(args):
             # max_off_iters = 30 objective evaluations (forward + backward) on the same particles
             comp["epoch_mix_states_per_s"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fwd_bwd_ms"]) * 1e-3)
             comp["epoch_mix_states_per_s_c_abi"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fused_call_ms"]) * 1e-3)
+            if comp.get("iw_fwd_bwd_graph_ms"):
+                comp["epoch_mix_states_per_s_graph"] = n / ((comp["search_ms"] + 30.0 * comp["iw_fwd_bwd_graph_ms"]) * 1e-3)
     # live launch count of one step (rank 0 launches the objective as well as its share of the search)
     if world > 1:
         dist.barrier()
@@ -664,9 +683,21 @@ def run_ours(args):
         bytes_iw = (36 + 20 * k) * n
         t_k = comp["iw_kernels_fwd_ms"] + comp["iw_kernels_bwd_ms"]
         gbs = bytes_iw / (t_k * 1e-3) / 1e9
+        # What actually paces the two gather kernels: every neighbour weight / reverse-neighbour gradient is a random
+        # 4-byte read of an L2-resident array (4 MB at N = 1M) and moves a whole 32-byte sector to the SM: 2 k N sectors
+        # per forward + backward on top of the streamed bytes (ncu: DRAM reads below the algorithmic bytes, 0 B written,
+        # profiles/r02_ncu_iw_kernels.txt).  Stated against the L2 throughput cap of the profiling guide
+        # (~6300 B/clk full chip) at the SM clock sampled during the timed region.
+        sector_bytes = 2 * k * n * 32
+        l2_cap = 6300.0 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1900.0) * 1e6 / 1e9
         comp["iw_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
                                "frac": gbs / peaks["hbm"], "algorithmic_bytes": bytes_iw, "kernel_ms": t_k,
-                               "note": "IW fwd (scan+gather) + bwd kernels through the C ABI; (36+20k) B/state"}
+                               "note": "IW fwd (scan+gather) + bwd kernels through the C ABI; (36+20k) B/state",
+                               "l2": {"sector_bytes_random_gathers": sector_bytes,
+                                      "achieved_gbs": (bytes_iw + sector_bytes) / (t_k * 1e-3) / 1e9,
+                                      "cap_gbs": l2_cap, "frac": (bytes_iw + sector_bytes) / (t_k * 1e-3) / 1e9 / l2_cap,
+                                      "note": "streamed bytes + 32-byte sectors of the 2kN random 4-byte gathers; the working "
+                                              "set is L2-resident, so this (not HBM) is the bound of the gather kernels"}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
