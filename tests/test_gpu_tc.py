@@ -279,3 +279,28 @@ def test_foreign_queries_with_large_norms_stay_exact(factor, variant, monkeypatc
     res = mepol_b200.knn_device(torch.from_numpy(x).cuda(), 5, queries=torch.from_numpy(q).cuda(), algo=_lib.KNN_TC)
     ref_d, ref_i = knn_oracle.knn_c(x, 5, queries=q, mode="kd_tree")
     assert_knn_matches(res.distances.cpu().numpy(), res.indices.cpu().numpy(), ref_d, ref_i, x, queries=q, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,clump", [(30011, 2), (30011, 6), (50021, 40), (66000, 3)])
+def test_survivor_path_branches_agree_with_simt(n, clump):
+    """The pruner's survivor handling has two routes: the usual one (every row of the warp has at most ONE
+    survivor in the tile: its value is the group minimum, nothing is parked) and the general one (parked
+    group + walk).  Index-adjacent near-duplicates put a row's nearest neighbours into the SAME 32-score
+    group of the SAME tile, clumps wider than 32 spread them over two groups, and n is not a multiple of
+    32 / 256 (ragged last group, padded last tile): every combination must give the exact answer."""
+    rng = np.random.default_rng(n + clump)
+    base = rng.standard_normal(((n + clump - 1) // clump, 29))
+    x = np.repeat(base, clump, axis=0)[:n] + 1e-3 * rng.standard_normal((n, 29))
+    x = torch.from_numpy(x.astype(np.float32)).cuda()
+    a = mepol_b200.knn_device(x, 5, algo=_lib.KNN_SIMT)
+    b = mepol_b200.knn_device(x, 5, algo=_lib.KNN_TC)
+    assert torch.equal(a.indices, b.indices)
+    assert torch.equal(a.distances, b.distances)
+    assert torch.equal(a.rk, b.rk)
+    if clump == 3 and n == 66000:        # and against the independent oracle on a sample of rows
+        from oracle import knn_oracle
+        rows = np.random.default_rng(0).choice(n, 300, replace=False)
+        xn = x.cpu().numpy()
+        ref_d, ref_i = knn_oracle.knn_c(xn, 5, queries=xn[rows], mode="kd_tree")
+        assert_knn_matches(b.distances.cpu().numpy()[rows], b.indices.cpu().numpy()[rows], ref_d, ref_i, xn,
+                           queries=xn[rows], rtol=1e-12)
