@@ -666,7 +666,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     for (int c = 0; c < kGroups; ++c) lg |= h2_any_lt(gm[c], tau2) ? (1u << c) : 0u;
                     const unsigned gbits = __reduce_or_sync(0xffffffffu, lg);
                     ep[0] += T2_NOW() - pt3;
-                    if (kSingle) {
+                    // (a row with TWO hit groups already rules the single-survivor path out: one vote, before any mask is
+                    // built -- that is nearly every entry of the ramp at the start of a unit, which otherwise paid for
+                    // the masks twice: prune kernel 0.098 -> 0.121 ms at N = 10,000 before this test)
+                    if (kSingle && !__any_sync(0xffffffffu, (lg & (lg - 1)) != 0)) {
                         // Common case once tau has settled: every row has at most ONE survivor in the whole tile.  One
                         // pass over the hit groups builds the masks; a row's survivor is its group minimum (already
                         // in the min tree), so nothing is parked and the deferred part is one predicated append.
