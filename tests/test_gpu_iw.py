@@ -146,13 +146,25 @@ def test_large_synthetic_batch_matches_oracle(dtype, tol):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-5)])
-def test_many_short_ragged_trajectories_use_the_warp_kernels(dtype, tol):
-    """>= 512 trajectories switches the scan / backward to the warp-per-trajectory kernels; ragged
-    lengths (incl. length 1 and > 128) exercise their chunking."""
+@pytest.mark.parametrize("flavour", ["short", "long", "aligned"])
+def test_many_short_ragged_trajectories_use_the_warp_kernels(dtype, tol, flavour):
+    """>= 512 trajectories switches the scan / backward to the warp-per-trajectory kernels (each lane owns 16
+    consecutive steps, one shuffle scan per 512 steps).  "short": ragged lengths incl. 1 and > 128 (unaligned scalar
+    loads, partly filled chunks); "long": trajectories beyond 512 steps (several blocks linked by the carry, incl.
+    exactly 512 / 513 / 1024 / 1025); "aligned": every offset a multiple of 4 (the 16-byte vector path) with lengths
+    that are and are not multiples of 16."""
     rng = np.random.default_rng(23)
     T, k, ns = 900, 4, 7
-    lens = rng.integers(1, 300, T)
-    lens[:3] = [1, 129, 257]
+    if flavour == "short":
+        lens = rng.integers(1, 300, T)
+        lens[:3] = [1, 129, 257]
+    elif flavour == "long":
+        T = 600
+        lens = rng.integers(1, 1500, T)
+        lens[:6] = [512, 513, 1024, 1025, 511, 1]
+    else:
+        lens = 4 * rng.integers(1, 200, T)
+        lens[:4] = [16, 512, 500, 4]
     n = int(lens.sum())
     idx = rng.integers(0, n, (n, k + 1)).astype(np.int32)
     idx[:, 0] = np.arange(n)
