@@ -583,7 +583,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                         continue;
                     }
                     tc_ld_packed_at<kSubRegs>(tmem_row + buf * NC, v + sbt * kSubRegs);
-                    {   // probe the next buffer's barrier while the TMEM load is in flight
+                    if (kBufs == 1) {
+                        // (N = 256 arrangement: no probing.  The accumulator is rarely back before this warp returns to
+                        // the wait, so the two non-blocking probes per tile of the two-buffer arrangement mostly failed
+                        // and only cost issue slots: -1.5 % at N = 512k-1M without them, neutral at 64k-131k.)
+                        next_ready = false;
+                    } else {   // probe the next buffer's barrier while the TMEM load is in flight
                         const uint32_t st1 = (its + 1) % kT2Stages;
                         next_ready = mbar_test_wait(my_done + 8 * st1, ((its + 1) / kT2Stages) & 1);
                     }
@@ -627,7 +632,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     const uint32_t m2 = hmin2_3(w[6], w[7], w[8]), m3 = hmin2_3(w[9], w[10], w[11]);
                     const uint32_t m4 = hmin2_3(w[12], w[13], w[14]);
                     gm[c] = hmin2_2(hmin2_3(m0, m1, m2), hmin2_3(m3, m4, w[15]));
-                    if (c == kGroups / 2 - 1 && !next_ready) {
+                    if (kBufs == 2 && c == kGroups / 2 - 1 && !next_ready) {
                         const uint32_t st1 = (it + kFuse) % kT2Stages;
                         next_ready = mbar_test_wait_after(my_done + 8 * st1, ((it + kFuse) / kT2Stages) & 1,
                                                           __uint_as_float(gm[c]));
