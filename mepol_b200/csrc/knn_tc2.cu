@@ -389,9 +389,17 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int my_base = rloc * kT2BufStride;
         const float A = glob[G_AMAX], D = glob[G_DELTA_MAX], AhalfMax = glob[G_AHALF_MAX], AtildeMax = glob[G_ATILDE_MAX];
         const float INF = __int_as_float(0x7f800000);
-        const uint32_t my_done = t == 0 ? bar_done0 : bar_done1;
-        const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
-        const uint32_t acc_empty_addr = bar_acc_empty + 16 * t;
+        uint32_t my_done = t == 0 ? bar_done0 : bar_done1;
+        uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
+        uint32_t acc_empty_addr = bar_acc_empty + 16 * t;
+        int lane0 = lane == 0 ? 1 : 0;
+        // this row's candidate buffers as pinned 32-bit shared addresses (appends are st.shared [addr + 4 cnt])
+        uint32_t bufv_row = smem_u32(bufv + my_base), bufi_row = smem_u32(bufi + my_base);
+        asm volatile("" : "+r"(bufv_row), "+r"(bufi_row));
+        // Pin the per-warp constants in registers: the compiler otherwise re-derives them inside EVERY tile iteration from
+        // special registers (S2R tid, S2UR cluster CTA id for the shared window, shifts, adds: ~15 instructions around the
+        // wait and the TMEM load).  Interleaved A/B: -6.4 % at N = 262k, -5.2 % at 1M (profiles/r02_tc2_notes.md).
+        asm volatile("" : "+r"(acc_empty_addr), "+r"(lane0), "+r"(my_done), "+r"(tmem_row));
         uint32_t *stg = reinterpret_cast<uint32_t *>(smem + kT2SmemStage) + warp * (32 * kT2StgStride);
         uint32_t it = 0;
         unsigned n_compactions = 0;
@@ -520,8 +528,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 if (kSingle && pend_single) {
                     if (mask && pend_val < tau) {
                         const int b = __ffs(mask) - 1;
-                        bufv[my_base + cnt] = pend_val;
-                        bufi[my_base + cnt] = pend_ref0 + 2 * (b & 15) + (b >> 4);
+                        // (explicit st.shared on the pinned row addresses: the C++ stores re-derived the row's address from
+                        // S2R tid / the shared-window base at every append; -1 % at N = 131k)
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bufv_row + 4u * (uint32_t)cnt), "f"(pend_val) : "memory");
+                        asm volatile("st.shared.s32 [%0], %1;" ::"r"(bufi_row + 4u * (uint32_t)cnt),
+                                     "r"(pend_ref0 + 2 * (b & 15) + (b >> 4))
+                                     : "memory");
                         ++cnt;
                         if (K1 > 0) {
                             topk_insert(pend_val);
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                     tc_wait_ld();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty_addr + 8 * buf);
+                    if (lane0 != 0) mbar_arrive(acc_empty_addr + 8 * buf);
                     pt2 = T2_NOW();
 #ifdef MEPOL_BRINGUP
                     if (t == 1 && lane == 0) atomicMax(const_cast<uint32_t *>(ts_s + 16 + (its & 7)), (uint32_t)pt2);   // last release
