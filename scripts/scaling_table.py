@@ -31,8 +31,10 @@ out += ["",
         f"column is flattered by clocks (with the single-GPU kernel scaled to the 8-GPU clock it would read {eq:.2f}); what does not shrink "
         f"with G is the replicated operand packing, the two collectives and rank 0's objective, ≈1.0 ms against an {k8:.1f} ms kernel.",
         "The 1-GPU and 8-GPU lines were taken back to back on the same box (GPU 0 of the 8); the 2- and 4-GPU lines on other boxes of the pool, "
-        "one commit earlier (log-prob H2D not yet under the search in the end-to-end arm). All four predate the last kernel change of the "
-        "round (no barrier probes in the epilogue, -1.5 % at N = 1M; `r02_bench_n1_final_kernel.json` is the 1-GPU line with it).",
+        "one commit earlier (log-prob H2D not yet under the search in the end-to-end arm). All four predate the last two kernel changes of the "
+        "round (no barrier probes in the epilogue, per-warp constants pinned in registers: together -6.5 % at N = 1M; "
+        "`r02_bench_n1_final_kernel.json` is the 1-GPU line with them: 67.7 ms, 15.48 M states/s, 0.70 of the peak). The 1-GPU row of the "
+        "sweep table below IS the final kernel; the 2/4/8-GPU rows are not.",
         "",
         "Sweep (`r02_sweep_{1,2,4,8}gpu.jsonl`, sampled-row oracle parity on every line; the 1-GPU file also carries a full sklearn "
         "search per N ≤ 262,144): per-GPU fraction of the sustained peak at N = 64k … 4M:",
