@@ -35,7 +35,7 @@
 //               accumulator, each wait on one address for the whole warp (uniform try_wait, no vote)
 //   warps 0-7   epilogue: warp w owns TMEM lanes 32*(w%4).. of accumulator w/4, one row per thread
 //
-// What the kernel is sensitive to (profiles/r02_tc2_notes.md sections 7-8): all of tensor memory is in flight, so the
+// What the kernel is sensitive to (profiles/r02_tc2_notes.md sections 7-9): all of tensor memory is in flight, so the
 // rate is TMEM capacity / the accumulator's round trip, and that round trip is paced half by the hand-shake and half
 // by the slowest of the four epilogue warps behind one release barrier.  The TMEM load is free, the min tree + vote are
 // 15 % of the kernel, the survivor entries 10 % at N = 1M and a third at N = 131k -- and the entry count is at its floor
